@@ -1,0 +1,127 @@
+/* ofdm_b200.h - C ABI of the B200-native OFDM link simulator (libofdm_b200.so).
+ *
+ * The reference (JomarJunior/ofdm-based-systems) is pure Python and has no FFI: its seam for this path
+ * is the class registry of `Simulation` (src/ofdm_based_systems/simulation/models.py:73-103) and the
+ * body of `Simulation.run()` between :454 and :606.  Every entry point below names the reference
+ * lines it replaces.  Plain pointers and sizes only; no torch types.  All functions return 0 on
+ * success or a negative OFDM_E* code; ofdm_b200_last_error() gives the message of the last failure on
+ * the calling thread.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ */
+#ifndef OFDM_B200_H
+#define OFDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDM_B200_ABI_VERSION 1
+
+enum { OFDM_OK = 0, OFDM_EINVAL = -1, OFDM_ECUDA = -2, OFDM_EUNSUPPORTED = -3, OFDM_ENOMEM = -4 };
+
+/* values of the reference's str-Enums (configuration/enums.py:4-67) as integers */
+enum { OFDM_PREFIX_NONE = 0, OFDM_PREFIX_CYCLIC = 1, OFDM_PREFIX_ZERO = 2 };
+enum { OFDM_MOD_OFDM = 0, OFDM_MOD_SC_OFDM = 1 };
+enum { OFDM_EQ_NONE = 0, OFDM_EQ_ZF = 1, OFDM_EQ_MMSE = 2 };
+enum { OFDM_SCHEME_QAM = 0, OFDM_SCHEME_PSK = 1 };
+enum { OFDM_NOISE_NONE = 0, OFDM_NOISE_C64 = 2, OFDM_NOISE_C128 = 3 };
+
+typedef struct ofdm_link ofdm_link; /* opaque: one configured link (tables resident in HBM) */
+
+/* What Simulation.run() fixes before its hot loop (simulation/models.py:226-410). */
+typedef struct ofdm_link_desc {
+  int32_t n_subcarriers; /* power of two, 8 .. 8192                       (num_subcarriers, :110)      */
+  int32_t prefix_type;   /* OFDM_PREFIX_*                                  (PREFIX_SCHEME_MAPPERS, :83) */
+  int32_t prefix_len;    /* int(prefix_length_ratio * channel.order)       (:251-253)                   */
+  int32_t modulator;     /* OFDM_MOD_*                                     (MODULATOR_SCHEME_MAPPERS)   */
+  int32_t equalizer;     /* OFDM_EQ_*                                      (EQUALIZATOR_SCHEME_MAPPERS) */
+  int32_t scheme;        /* OFDM_SCHEME_*                                  (CONSTELLATION_SCHEME_..)    */
+  int32_t n_taps;        /* 1 .. 32                                                                      */
+  int32_t device;        /* CUDA device ordinal, -1 = the calling thread's current device               */
+} ofdm_link_desc;
+
+typedef struct ofdm_link_result {
+  uint64_t bit_errors;    /* simulation/models.py:597                                   */
+  uint64_t bits;          /* bits actually compared                                     */
+  uint64_t symbol_errors; /* :604-606                                                   */
+  uint64_t symbols;       /* constellation symbols compared (inactive subcarriers too)  */
+  uint64_t ofdm_symbols;
+  uint64_t tx_samples;    /* ofdm_symbols * (N + P)                                     */
+  double tx_power_sum;    /* sum |tx|^2 over every tx sample, prefix included (:519-522) */
+  double tx_power_max;    /* max |tx|^2                                                  */
+} ofdm_link_result;
+
+/* Optional per-symbol dumps (device or host memory, see the call); any pointer may be NULL. */
+typedef struct ofdm_link_dump {
+  float* y;            /* [n_symbols][N] complex64: ortho FFT output before the equaliser            */
+  float* z;            /* [n_symbols][N] complex64: what the demapper sees (results["received_symbols"]) */
+  uint16_t* rx_labels; /* [n_symbols][N]                                                             */
+  uint16_t* tx_labels; /* [n_symbols][N]                                                             */
+  float* noise;        /* [n_symbols][N+P] complex64: the noise the fused mode generated             */
+} ofdm_link_dump;
+
+const char* ofdm_b200_last_error(void);
+int ofdm_b200_abi_version(void);
+/* number of CUDA devices visible, <0 on error (used by the host side to fail loudly without a GPU) */
+int ofdm_b200_device_count(void);
+
+/* Build one link: uploads the channel taps, the equaliser table and the per-subcarrier loading.
+ *   taps_chan : n_taps complex128 (re,im interleaved), ALREADY unit energy  (channel/models.py:14-16,37-44)
+ *   h_eq      : N complex128, the equaliser's frequency response = fft(RAW taps, N) (simulation/models.py:263-266)
+ *   orders    : N constellation orders, 0 = subcarrier carries nothing (constellation/adaptive.py:52-80);
+ *               a constant array reproduces the fixed mapper (constellation/models.py:150-321)
+ *   amp       : N tx amplitude scale factors applied on top of the unit-power constellation, or NULL
+ */
+int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const double* h_eq,
+                     const int32_t* orders, const double* amp, ofdm_link** out);
+void ofdm_link_destroy(ofdm_link* link);
+int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* link);
+
+/* Fused Monte-Carlo mode: replaces simulation/models.py:454-606 for OFDM symbols
+ * [first_symbol, first_symbol + n_symbols) of SNR point `point`; bits and AWGN come from
+ * Philox4x32-10 keyed by `seed` with counter (symbol, stream, point), so any sharding of the symbol
+ * range over GPUs produces the same union.  noise_sigma is the per-component standard deviation
+ * sqrt(mean|stream|^2 / snr_lin / 2) (noise/models.py:14-20), computed by the caller.
+ * Synchronous: returns when `out` is filled.  dump pointers, if given, are HOST memory. */
+int ofdm_link_run_fused(ofdm_link* link, double snr_db, double noise_sigma, uint64_t seed, uint32_t point,
+                        uint64_t first_symbol, uint64_t n_symbols, const ofdm_link_dump* dump,
+                        ofdm_link_result* out);
+
+/* Replay mode with HOST buffers: identical bits / noise as fed to the reference.
+ *   bits  : the BytesIO content of generate_bits (bits_generation/models.py:27-55), MSB first
+ *   noise : complex noise over the serial stream, (N+P) samples per OFDM symbol, as added by
+ *           AWGNoiseModel.add_noise (noise/models.py:19-22); dtype OFDM_NOISE_C64 / _C128 / _NONE
+ *   compare_limit_bits : bit positions >= this are not compared (zip() truncation, simulation/models.py:597);
+ *                        0 = compare everything
+ * Copies inputs to the device, runs, copies results (and dumps) back. */
+int ofdm_link_run_replay(ofdm_link* link, double snr_db, const uint8_t* bits, uint64_t n_bytes,
+                         const void* noise, int32_t noise_dtype, uint64_t n_symbols,
+                         uint64_t compare_limit_bits, const ofdm_link_dump* dump, ofdm_link_result* out);
+
+/* Asynchronous variants on DEVICE memory: enqueue on `stream` (a cudaStream_t, NULL = legacy default),
+ * accumulate into the link's device-resident counters; ofdm_link_read_result synchronises the stream,
+ * returns the totals since the last ofdm_link_reset_counters and leaves them untouched. */
+int ofdm_link_launch_fused(ofdm_link* link, double snr_db, double noise_sigma, uint64_t seed, uint32_t point,
+                           uint64_t first_symbol, uint64_t n_symbols, const ofdm_link_dump* dump_dev,
+                           void* stream);
+int ofdm_link_launch_replay(ofdm_link* link, double snr_db, const uint8_t* bits_dev, uint64_t n_bytes,
+                            const void* noise_dev, int32_t noise_dtype, uint64_t n_symbols,
+                            uint64_t compare_limit_bits, const ofdm_link_dump* dump_dev, void* stream);
+int ofdm_link_reset_counters(ofdm_link* link, void* stream);
+int ofdm_link_read_result(ofdm_link* link, void* stream, ofdm_link_result* out);
+/* device address of the raw counter block (8 x uint64, then double sum, then uint64 max bits): lets the
+ * multi-GPU host side all-reduce the counters in place with NCCL */
+void* ofdm_link_counters_device_ptr(ofdm_link* link);
+/* kernel launches issued by this library since load (for bench.py's gpu_launches) */
+uint64_t ofdm_b200_launch_count(void);
+
+/* FP32 FFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per FFMA) on the current device,
+ * the roofline denominator SURVEY 8(d) asks for; <0 on error. */
+double ofdm_b200_measure_fp32_tflops(int32_t iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDM_B200_H */

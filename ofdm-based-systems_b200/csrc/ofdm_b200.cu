@@ -1,0 +1,435 @@
+// C ABI of libofdm_b200.so (see include/ofdm_b200.h): host-side plan building in fp64, kernel
+// dispatch, host<->device staging for the host-buffer entry points.
+#include "../../include/ofdm_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "plan.h"
+
+using namespace ofdm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+}  // namespace
+
+namespace ofdm {
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace ofdm
+
+namespace {
+
+int configure(ofdm_link* L) {
+  switch (L->d.n_subcarriers) {
+#define X(n) case n: return configure_kernel<n>(L);
+    OFDM_FOR_EACH_N(X)
+#undef X
+    default: return fail(OFDM_EUNSUPPORTED, "n_subcarriers=%d: only powers of two in 8..8192 have a CUDA plan", L->d.n_subcarriers);
+  }
+}
+
+int launch(const ofdm_link* L, const LinkParams& p, cudaStream_t stream) {
+  switch (L->d.n_subcarriers) {
+#define X(n) case n: return launch_kernel<n>(L, p, stream);
+    OFDM_FOR_EACH_N(X)
+#undef X
+    default: return fail(OFDM_EUNSUPPORTED, "n_subcarriers=%d unsupported", L->d.n_subcarriers);
+  }
+}
+
+// Inter-pass twiddles of the Stockham plan in link_kernel.cuh (forward sign):
+//   pass 2 (radix R2, NS = R1):     tw[(r-1)*(N/R2) + j]       = exp(-2 pi i (j mod NS) r / (NS R2))
+//   pass 3 (radix R3, NS = R1*R2):  tw[TW2 + (r-1)*(N/R3) + j] likewise
+std::vector<float2> build_twiddles(int N, int E) {
+  const int R1 = E, rem = N / R1, R2 = rem < E ? rem : E, R3 = rem / R2;
+  std::vector<float2> tw;
+  auto add_pass = [&](int R, int NS) {
+    if (R <= 1) return;
+    const int NB = N / R;
+    const size_t base = tw.size();
+    tw.resize(base + size_t(R - 1) * NB);
+    for (int r = 1; r < R; ++r)
+      for (int j = 0; j < NB; ++j) {
+        const int k = j % NS;
+        const double ang = -2.0 * M_PI * double((long long)k * r % (long long)(NS * R)) / double(NS * R);
+        tw[base + size_t(r - 1) * NB + j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      }
+  };
+  add_pass(R2, R1);
+  add_pass(R3, R1 * R2);
+  if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+  return tw;
+}
+
+void fill_params(const ofdm_link* L, LinkParams& p, double snr_db) {
+  std::memset(&p, 0, sizeof(p));
+  p.prefix_len = L->d.prefix_len;
+  p.prefix_type = L->d.prefix_type;
+  p.modulator = L->d.modulator;
+  p.equalizer = L->d.equalizer;
+  p.scheme = L->d.scheme;
+  p.n_taps = L->d.n_taps;
+  p.isi = L->isi;
+  std::memcpy(p.taps, L->taps, sizeof(p.taps));
+  p.sc_tab = L->d_sc;
+  p.eq_tab = L->d_eq;
+  p.tw = L->d_tw;
+  const double snr_lin = std::pow(10.0, snr_db / 10.0);
+  // equalization/models.py:43-49: sigma2 = mean|Y|^2 / snr_lin / mean|H|^2, inf if the gain is zero
+  p.mmse_c = L->mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(L->d.n_subcarriers) * snr_lin * L->mean_h2));
+  p.bits_per_ofdm = (unsigned)L->bits_per_ofdm;
+  p.counters = L->d_cnt->cnt;
+  p.tx_power_sum = &L->d_cnt->power_sum;
+  p.tx_power_max_bits = &L->d_cnt->power_max_bits;
+}
+
+void set_dump(LinkParams& p, const ofdm_link_dump* d) {
+  if (!d) return;
+  p.dump_y = reinterpret_cast<float2*>(d->y);
+  p.dump_z = reinterpret_cast<float2*>(d->z);
+  p.dump_rx = d->rx_labels;
+  p.dump_tx = d->tx_labels;
+  p.dump_noise = reinterpret_cast<float2*>(d->noise);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != prev && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// host-side mirror of the dump block with device buffers behind it
+struct DumpStage {
+  ofdm_link_dump dev{};
+  const ofdm_link_dump* host = nullptr;
+  size_t n_sym = 0;
+  int N = 0, NP = 0;
+  int alloc(const ofdm_link_dump* h, size_t n_symbols, int n, int np) {
+    host = h;
+    n_sym = n_symbols;
+    N = n;
+    NP = np;
+    if (!h) return OFDM_OK;
+    if (h->y) CUDA_TRY(cudaMalloc(&dev.y, n_sym * N * sizeof(float2)));
+    if (h->z) CUDA_TRY(cudaMalloc(&dev.z, n_sym * N * sizeof(float2)));
+    if (h->rx_labels) CUDA_TRY(cudaMalloc(&dev.rx_labels, n_sym * N * sizeof(uint16_t)));
+    if (h->tx_labels) CUDA_TRY(cudaMalloc(&dev.tx_labels, n_sym * N * sizeof(uint16_t)));
+    if (h->noise) {
+      CUDA_TRY(cudaMalloc(&dev.noise, n_sym * NP * sizeof(float2)));
+      CUDA_TRY(cudaMemset(dev.noise, 0, n_sym * NP * sizeof(float2)));
+    }
+    return OFDM_OK;
+  }
+  int fetch() {
+    if (!host) return OFDM_OK;
+    if (host->y) CUDA_TRY(cudaMemcpy(host->y, dev.y, n_sym * N * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (host->z) CUDA_TRY(cudaMemcpy(host->z, dev.z, n_sym * N * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (host->rx_labels)
+      CUDA_TRY(cudaMemcpy(host->rx_labels, dev.rx_labels, n_sym * N * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (host->tx_labels)
+      CUDA_TRY(cudaMemcpy(host->tx_labels, dev.tx_labels, n_sym * N * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (host->noise) CUDA_TRY(cudaMemcpy(host->noise, dev.noise, n_sym * NP * sizeof(float2), cudaMemcpyDeviceToHost));
+    return OFDM_OK;
+  }
+  ~DumpStage() {
+    cudaFree(dev.y);
+    cudaFree(dev.z);
+    cudaFree(dev.rx_labels);
+    cudaFree(dev.tx_labels);
+    cudaFree(dev.noise);
+  }
+};
+
+int read_counters(ofdm_link* L, cudaStream_t stream, ofdm_link_result* out) {
+  CounterBlock h;
+  CUDA_TRY(cudaMemcpyAsync(&h, L->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  out->bit_errors = h.cnt[CNT_BIT_ERRORS];
+  out->bits = h.cnt[CNT_BITS];
+  out->symbol_errors = h.cnt[CNT_SYM_ERRORS];
+  out->symbols = h.cnt[CNT_SYMBOLS];
+  out->ofdm_symbols = h.cnt[CNT_OFDM_SYMBOLS];
+  out->tx_samples = h.cnt[CNT_OFDM_SYMBOLS] * (uint64_t)(L->d.n_subcarriers + L->d.prefix_len);
+  out->tx_power_sum = h.power_sum;
+  double mx;
+  std::memcpy(&mx, &h.power_max_bits, sizeof(mx));
+  out->tx_power_max = mx;
+  return OFDM_OK;
+}
+
+__global__ void ffma_chain_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+        x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456f) out[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ofdm_b200_last_error(void) { return g_err; }
+int ofdm_b200_abi_version(void) { return OFDM_B200_ABI_VERSION; }
+uint64_t ofdm_b200_launch_count(void) { return g_launches.load(); }
+
+int ofdm_b200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail(OFDM_ECUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return OFDM_ECUDA;
+  }
+  return n;
+}
+
+int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const double* h_eq, const int32_t* orders,
+                     const double* amp, ofdm_link** out) {
+  if (!desc || !taps_chan || !h_eq || !orders || !out) return fail(OFDM_EINVAL, "null argument");
+  const int N = desc->n_subcarriers, Lt = desc->n_taps, P = desc->prefix_len;
+  if (N < 8 || N > 8192 || (N & (N - 1))) return fail(OFDM_EUNSUPPORTED, "n_subcarriers=%d: need a power of two in 8..8192", N);
+  if (Lt < 1 || Lt > kMaxTaps) return fail(OFDM_EUNSUPPORTED, "n_taps=%d: need 1..%d", Lt, kMaxTaps);
+  if (Lt - 1 > N) return fail(OFDM_EUNSUPPORTED, "channel longer than one OFDM symbol");
+  if (P < 0 || P > N) return fail(OFDM_EINVAL, "prefix_len=%d: need 0..N", P);
+  if (desc->prefix_type < 0 || desc->prefix_type > 2 || desc->modulator < 0 || desc->modulator > 1 ||
+      desc->equalizer < 0 || desc->equalizer > 2 || desc->scheme < 0 || desc->scheme > 1)
+    return fail(OFDM_EINVAL, "enum value out of range");
+  if (desc->prefix_type == OFDM_PREFIX_NONE && P != 0) return fail(OFDM_EINVAL, "prefix NONE needs prefix_len 0");
+
+  int dev = desc->device;
+  if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+  DeviceGuard guard(dev);
+
+  ofdm_link* L = new ofdm_link();
+  L->d = *desc;
+  L->device = dev;
+  // consecutive OFDM symbols interact when the prefix is shorter than the channel memory
+  L->isi = (Lt - 1 > P) ? 1 : 0;
+  for (int l = 0; l < kMaxTaps; ++l)
+    L->taps[l] = l < Lt ? make_float2((float)taps_chan[2 * l], (float)taps_chan[2 * l + 1]) : make_float2(0.f, 0.f);
+
+  std::vector<float4> sc(N), eq(N);
+  int bit_off = 0;
+  double sum_h2 = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const int M = orders[k];
+    int bps = 0;
+    if (M < 0 || (M & (M - 1)) || M > 65536) { delete L; return fail(OFDM_EINVAL, "orders[%d]=%d is not a power of two", k, M); }
+    while ((1 << bps) < M) ++bps;
+    if (M <= 1) bps = 0;
+    if (desc->scheme == OFDM_SCHEME_QAM && (bps & 1)) { delete L; return fail(OFDM_EINVAL, "orders[%d]=%d: QAM order must be a perfect square", k, M); }
+    const double knorm = desc->scheme == OFDM_SCHEME_QAM && M > 1 ? std::sqrt(2.0 * (M - 1) / 3.0) : 1.0;
+    const double a = (amp ? amp[k] : 1.0);
+    const unsigned info = (unsigned)bps | ((unsigned)bit_off << 8);
+    float info_f;
+    std::memcpy(&info_f, &info, 4);
+    sc[k] = make_float4((float)(a / knorm), (float)knorm, info_f, 0.f);
+    bit_off += bps;
+    const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
+    sum_h2 += std::norm(H);
+    if (desc->equalizer == OFDM_EQ_ZF) {
+      // equalization/models.py:33-35: h = where(H == 0, 1e-10, H); Z = Y / h
+      const std::complex<double> h = (H == std::complex<double>(0.0, 0.0)) ? std::complex<double>(1e-10, 0.0) : H;
+      const std::complex<double> inv = 1.0 / h;
+      eq[k] = make_float4((float)inv.real(), (float)inv.imag(), 0.f, 0.f);
+    } else {
+      eq[k] = make_float4((float)H.real(), (float)H.imag(), (float)std::norm(H), 0.f);
+    }
+  }
+  L->bits_per_ofdm = bit_off;
+  L->mean_h2 = sum_h2 / N;
+
+  int rc = configure(L);
+  if (rc != OFDM_OK) { delete L; return rc; }
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  L->sms = prop.multiProcessorCount;
+
+  const std::vector<float2> tw = build_twiddles(N, L->E);
+  CUDA_TRY(cudaMalloc(&L->d_sc, N * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&L->d_eq, N * sizeof(float4)));
+  CUDA_TRY(cudaMalloc(&L->d_tw, tw.size() * sizeof(float2)));
+  CUDA_TRY(cudaMalloc(&L->d_cnt, sizeof(CounterBlock)));
+  CUDA_TRY(cudaMemcpy(L->d_sc, sc.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L->d_eq, eq.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(L->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(L->d_cnt, 0, sizeof(CounterBlock)));
+  *out = L;
+  return OFDM_OK;
+}
+
+void ofdm_link_destroy(ofdm_link* L) {
+  if (!L) return;
+  DeviceGuard guard(L->device);
+  cudaFree(L->d_sc);
+  cudaFree(L->d_eq);
+  cudaFree(L->d_tw);
+  cudaFree(L->d_cnt);
+  delete L;
+}
+
+int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* L) { return L ? L->bits_per_ofdm : OFDM_EINVAL; }
+void* ofdm_link_counters_device_ptr(ofdm_link* L) { return L ? (void*)L->d_cnt : nullptr; }
+
+int ofdm_link_reset_counters(ofdm_link* L, void* stream) {
+  if (!L) return fail(OFDM_EINVAL, "null link");
+  DeviceGuard guard(L->device);
+  CUDA_TRY(cudaMemsetAsync(L->d_cnt, 0, sizeof(CounterBlock), (cudaStream_t)stream));
+  return OFDM_OK;
+}
+
+int ofdm_link_read_result(ofdm_link* L, void* stream, ofdm_link_result* out) {
+  if (!L || !out) return fail(OFDM_EINVAL, "null argument");
+  DeviceGuard guard(L->device);
+  return read_counters(L, (cudaStream_t)stream, out);
+}
+
+int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint64_t seed, uint32_t point,
+                           uint64_t first_symbol, uint64_t n_symbols, const ofdm_link_dump* dump_dev, void* stream) {
+  if (!L) return fail(OFDM_EINVAL, "null link");
+  if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
+  DeviceGuard guard(L->device);
+  LinkParams p;
+  fill_params(L, p, snr_db);
+  p.bits_src = SRC_PHILOX;
+  p.noise_src = noise_sigma > 0.0 ? SRC_PHILOX : SRC_NONE;
+  p.sigma = (float)noise_sigma;
+  p.seed = seed;
+  p.point = point;
+  p.sym_begin = first_symbol;
+  p.sym_count = n_symbols;
+  set_dump(p, dump_dev);
+  return launch(L, p, (cudaStream_t)stream);
+}
+
+int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev, uint64_t n_bytes, const void* noise_dev,
+                            int32_t noise_dtype, uint64_t n_symbols, uint64_t compare_limit_bits,
+                            const ofdm_link_dump* dump_dev, void* stream) {
+  if (!L || !bits_dev) return fail(OFDM_EINVAL, "null argument");
+  if (noise_dtype != OFDM_NOISE_NONE && noise_dtype != OFDM_NOISE_C64 && noise_dtype != OFDM_NOISE_C128)
+    return fail(OFDM_EINVAL, "noise_dtype=%d", noise_dtype);
+  if (noise_dtype != OFDM_NOISE_NONE && !noise_dev) return fail(OFDM_EINVAL, "noise buffer missing");
+  if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
+  DeviceGuard guard(L->device);
+  LinkParams p;
+  fill_params(L, p, snr_db);
+  p.bits_src = SRC_REPLAY_F32;
+  p.noise_src = noise_dtype;
+  p.bits = bits_dev;
+  p.bits_len = n_bytes;
+  p.noise = noise_dev;
+  p.sym_begin = 0;
+  p.sym_count = n_symbols;
+  p.limit_bits = compare_limit_bits != 0;
+  p.compare_limit = compare_limit_bits;
+  set_dump(p, dump_dev);
+  return launch(L, p, (cudaStream_t)stream);
+}
+
+int ofdm_link_run_fused(ofdm_link* L, double snr_db, double noise_sigma, uint64_t seed, uint32_t point,
+                        uint64_t first_symbol, uint64_t n_symbols, const ofdm_link_dump* dump, ofdm_link_result* out) {
+  if (!L || !out) return fail(OFDM_EINVAL, "null argument");
+  DeviceGuard guard(L->device);
+  DumpStage stage;
+  int rc = stage.alloc(dump, n_symbols, L->d.n_subcarriers, L->d.n_subcarriers + L->d.prefix_len);
+  if (rc) return rc;
+  if ((rc = ofdm_link_reset_counters(L, nullptr))) return rc;
+  if ((rc = ofdm_link_launch_fused(L, snr_db, noise_sigma, seed, point, first_symbol, n_symbols, dump ? &stage.dev : nullptr, nullptr)))
+    return rc;
+  if ((rc = read_counters(L, nullptr, out))) return rc;
+  return stage.fetch();
+}
+
+int ofdm_link_run_replay(ofdm_link* L, double snr_db, const uint8_t* bits, uint64_t n_bytes, const void* noise,
+                         int32_t noise_dtype, uint64_t n_symbols, uint64_t compare_limit_bits,
+                         const ofdm_link_dump* dump, ofdm_link_result* out) {
+  if (!L || !out || !bits) return fail(OFDM_EINVAL, "null argument");
+  DeviceGuard guard(L->device);
+  const size_t np = L->d.n_subcarriers + L->d.prefix_len;
+  const size_t noise_bytes = noise_dtype == OFDM_NOISE_C64 ? n_symbols * np * 8 : noise_dtype == OFDM_NOISE_C128 ? n_symbols * np * 16 : 0;
+  uint8_t* d_bits = nullptr;
+  void* d_noise = nullptr;
+  DumpStage stage;
+  int rc = stage.alloc(dump, n_symbols, L->d.n_subcarriers, (int)np);
+  if (rc) return rc;
+  CUDA_TRY(cudaMalloc(&d_bits, n_bytes ? n_bytes : 1));
+  if (noise_bytes) {
+    if (!noise) { cudaFree(d_bits); return fail(OFDM_EINVAL, "noise buffer missing"); }
+    cudaError_t e = cudaMalloc(&d_noise, noise_bytes);
+    if (e != cudaSuccess) { cudaFree(d_bits); return fail(OFDM_ENOMEM, "cudaMalloc(noise) failed: %s", cudaGetErrorString(e)); }
+  }
+  auto cleanup = [&]() { cudaFree(d_bits); cudaFree(d_noise); };
+  cudaError_t e = cudaMemcpy(d_bits, bits, n_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && noise_bytes) e = cudaMemcpy(d_noise, noise, noise_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cleanup(); return fail(OFDM_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+  rc = ofdm_link_reset_counters(L, nullptr);
+  if (!rc) rc = ofdm_link_launch_replay(L, snr_db, d_bits, n_bytes, d_noise, noise_dtype, n_symbols, compare_limit_bits,
+                                        dump ? &stage.dev : nullptr, nullptr);
+  if (!rc) rc = read_counters(L, nullptr, out);
+  if (!rc) rc = stage.fetch();
+  cleanup();
+  return rc;
+}
+
+double ofdm_b200_measure_fp32_tflops(int32_t iters) {
+  if (iters <= 0) iters = 4096;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    fail(OFDM_ECUDA, "no CUDA device");
+    return -1.0;
+  }
+  float* d = nullptr;
+  if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    ffma_chain_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) { best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    const double flops = 2.0 * 8.0 * 16.0 * double(iters) * double(blocks) * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Shared between the C-ABI translation unit (ofdm_b200.cu) and the per-size kernel instantiation
+// units (link_inst.cu, compiled once per supported N so the build parallelises).
+#pragma once
+#include "../../include/ofdm_b200.h"
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "link_params.h"
+
+namespace ofdm {
+
+constexpr int elements_per_thread(int n) {
+  return n <= 8 ? 8 : n == 16 ? 4 : n <= 64 ? 8 : n <= 256 ? 16 : 32;
+}
+
+struct CounterBlock {  // device-resident accumulator, 80 bytes
+  unsigned long long cnt[CNT_WORDS];
+  double power_sum;
+  unsigned long long power_max_bits;
+};
+
+int fail(int code, const char* fmt, ...);
+void count_launch();
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return ::ofdm::fail(OFDM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+}  // namespace ofdm
+
+struct ofdm_link {
+  ofdm_link_desc d;
+  int E = 0, T = 0, block = 0, teams = 0;
+  int bits_per_ofdm = 0;
+  int isi = 0;
+  double mean_h2 = 0.0;
+  float2 taps[ofdm::kMaxTaps];
+  float4* d_sc = nullptr;
+  float4* d_eq = nullptr;
+  float2* d_tw = nullptr;
+  ofdm::CounterBlock* d_cnt = nullptr;
+  int device = 0, sms = 0, occ = 1;
+  size_t smem = 0;
+};
+
+namespace ofdm {
+// defined in link_inst.cu, one explicit instantiation per supported size
+template <int N> int configure_kernel(ofdm_link* L);
+template <int N> int launch_kernel(const ofdm_link* L, const LinkParams& p, cudaStream_t stream);
+}  // namespace ofdm
+
+#define OFDM_FOR_EACH_N(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)

@@ -1,0 +1,246 @@
+"""ctypes binding of libofdm_b200.so (C ABI in include/ofdm_b200.h).
+
+This is the ONLY compute backend of ``Simulation.run()`` and of the sweep runner: there is no CPU
+fallback.  Importing this module without the built library raises; using it without a CUDA device
+raises ``RuntimeError`` at the first call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.environ.get("OFDM_B200_LIB", os.path.join(_PKG_ROOT, "libofdm_b200.so"))
+
+PREFIX = {"NONE": 0, "CYCLIC": 1, "ZERO": 2}
+MODULATOR = {"OFDM": 0, "SC-OFDM": 1, "SC_OFDM": 1}
+EQUALIZER = {"NONE": 0, "ZF": 1, "MMSE": 2}
+SCHEME = {"QAM": 0, "PSK": 1}
+NOISE_NONE, NOISE_C64, NOISE_C128 = 0, 2, 3
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class LinkDesc(C.Structure):
+    _fields_ = [("n_subcarriers", C.c_int32), ("prefix_type", C.c_int32), ("prefix_len", C.c_int32),
+                ("modulator", C.c_int32), ("equalizer", C.c_int32), ("scheme", C.c_int32),
+                ("n_taps", C.c_int32), ("device", C.c_int32)]
+
+
+class LinkResult(C.Structure):
+    _fields_ = [("bit_errors", C.c_uint64), ("bits", C.c_uint64), ("symbol_errors", C.c_uint64),
+                ("symbols", C.c_uint64), ("ofdm_symbols", C.c_uint64), ("tx_samples", C.c_uint64),
+                ("tx_power_sum", C.c_double), ("tx_power_max", C.c_double)]
+
+
+class LinkDump(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("z", C.c_void_p), ("rx_labels", C.c_void_p), ("tx_labels", C.c_void_p),
+                ("noise", C.c_void_p)]
+
+
+EXPORTS = (
+    "ofdm_b200_last_error", "ofdm_b200_abi_version", "ofdm_b200_device_count", "ofdm_b200_launch_count",
+    "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol",
+    "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
+    "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr",
+)
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} is missing: build it with `python ofdm-based-systems_b200/build_native.py` "
+            "(the OFDM link has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_double
+    lib.ofdm_b200_last_error.restype = C.c_char_p
+    lib.ofdm_b200_abi_version.restype = i32
+    lib.ofdm_b200_device_count.restype = i32
+    lib.ofdm_b200_launch_count.restype = u64
+    lib.ofdm_b200_measure_fp32_tflops.restype = dbl
+    lib.ofdm_b200_measure_fp32_tflops.argtypes = [i32]
+    lib.ofdm_link_create.argtypes = [C.POINTER(LinkDesc), vp, vp, vp, vp, C.POINTER(vp)]
+    lib.ofdm_link_destroy.argtypes = [vp]
+    lib.ofdm_link_destroy.restype = None
+    lib.ofdm_link_bits_per_ofdm_symbol.argtypes = [vp]
+    lib.ofdm_link_run_fused.argtypes = [vp, dbl, dbl, u64, u32, u64, u64, C.POINTER(LinkDump), C.POINTER(LinkResult)]
+    lib.ofdm_link_run_replay.argtypes = [vp, dbl, vp, u64, vp, i32, u64, u64, C.POINTER(LinkDump), C.POINTER(LinkResult)]
+    lib.ofdm_link_launch_fused.argtypes = [vp, dbl, dbl, u64, u32, u64, u64, C.POINTER(LinkDump), vp]
+    lib.ofdm_link_launch_replay.argtypes = [vp, dbl, vp, u64, vp, i32, u64, u64, C.POINTER(LinkDump), vp]
+    lib.ofdm_link_reset_counters.argtypes = [vp, vp]
+    lib.ofdm_link_read_result.argtypes = [vp, vp, C.POINTER(LinkResult)]
+    lib.ofdm_link_counters_device_ptr.argtypes = [vp]
+    lib.ofdm_link_counters_device_ptr.restype = vp
+    if lib.ofdm_b200_abi_version() != 1:
+        raise NativeLibraryMissing(f"{LIB_PATH}: ABI version {lib.ofdm_b200_abi_version()} != 1, rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return (lib.ofdm_b200_last_error() or b"").decode()
+
+
+def device_count() -> int:
+    return int(lib.ofdm_b200_device_count())
+
+
+def require_gpu() -> None:
+    n = device_count()
+    if n <= 0:
+        raise RuntimeError("ofdm_based_systems needs a CUDA device (B200): the link chain runs only in "
+                           f"libofdm_b200.so and has no CPU fallback ({last_error() or 'no device found'})")
+
+
+def _check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc in (-1, -3):
+        raise ValueError(msg)
+    if rc == -4:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+@dataclass
+class LinkCounters:
+    bit_errors: int
+    bits: int
+    symbol_errors: int
+    symbols: int
+    ofdm_symbols: int
+    tx_samples: int
+    tx_power_sum: float
+    tx_power_max: float
+
+    @property
+    def papr_db(self) -> float:
+        """simulation/models.py:519-522."""
+        if self.tx_samples == 0 or self.tx_power_sum <= 0:
+            return float("inf")
+        return float(10 * np.log10(self.tx_power_max / (self.tx_power_sum / self.tx_samples)))
+
+    @classmethod
+    def from_struct(cls, r: LinkResult) -> "LinkCounters":
+        return cls(r.bit_errors, r.bits, r.symbol_errors, r.symbols, r.ofdm_symbols, r.tx_samples,
+                   r.tx_power_sum, r.tx_power_max)
+
+
+class Link:
+    """One configured link resident on one GPU (ofdm_link_create)."""
+
+    def __init__(self, n_subcarriers: int, taps_chan: np.ndarray, h_eq: np.ndarray, orders: np.ndarray, *,
+                 prefix_type: str = "CYCLIC", prefix_len: int = 0, modulator: str = "OFDM", equalizer: str = "MMSE",
+                 scheme: str = "QAM", amp: Optional[np.ndarray] = None, device: int = -1):
+        require_gpu()
+        taps = np.ascontiguousarray(taps_chan, dtype=np.complex128)
+        heq = np.ascontiguousarray(h_eq, dtype=np.complex128)
+        ords = np.ascontiguousarray(orders, dtype=np.int32)
+        if heq.shape != (n_subcarriers,) or ords.shape != (n_subcarriers,):
+            raise ValueError("h_eq and orders must have one entry per subcarrier")
+        a = None if amp is None else np.ascontiguousarray(amp, dtype=np.float64)
+        self.n_subcarriers, self.prefix_len = int(n_subcarriers), int(prefix_len)
+        self.desc = LinkDesc(n_subcarriers, PREFIX[prefix_type], prefix_len, MODULATOR[modulator], EQUALIZER[equalizer],
+                             SCHEME[scheme], taps.shape[0], device)
+        self._h = C.c_void_p()
+        _check(lib.ofdm_link_create(C.byref(self.desc), taps.ctypes.data, heq.ctypes.data, ords.ctypes.data,
+                                    None if a is None else a.ctypes.data, C.byref(self._h)))
+        self.bits_per_ofdm_symbol = int(lib.ofdm_link_bits_per_ofdm_symbol(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.ofdm_link_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- host-buffer entry points (synchronous)
+    def _dump_arrays(self, n_symbols: int, want: Optional[tuple]):
+        if not want:
+            return None, {}
+        n, npre = self.n_subcarriers, self.n_subcarriers + self.prefix_len
+        arrs = {}
+        if "y" in want:
+            arrs["y"] = np.zeros((n_symbols, n), dtype=np.complex64)
+        if "z" in want:
+            arrs["z"] = np.zeros((n_symbols, n), dtype=np.complex64)
+        if "rx_labels" in want:
+            arrs["rx_labels"] = np.zeros((n_symbols, n), dtype=np.uint16)
+        if "tx_labels" in want:
+            arrs["tx_labels"] = np.zeros((n_symbols, n), dtype=np.uint16)
+        if "noise" in want:
+            arrs["noise"] = np.zeros((n_symbols, npre), dtype=np.complex64)
+        d = LinkDump(*[arrs[k].ctypes.data if k in arrs else None for k in ("y", "z", "rx_labels", "tx_labels", "noise")])
+        return d, arrs
+
+    def run_fused(self, snr_db: float, noise_sigma: float, n_symbols: int, *, seed: int = 0x0FD3, point: int = 0,
+                  first_symbol: int = 0, dump: Optional[tuple] = None):
+        d, arrs = self._dump_arrays(n_symbols, dump)
+        res = LinkResult()
+        _check(lib.ofdm_link_run_fused(self._h, snr_db, noise_sigma, seed, point, first_symbol, n_symbols,
+                                       None if d is None else C.byref(d), C.byref(res)))
+        out = LinkCounters.from_struct(res)
+        return (out, arrs) if dump else out
+
+    def run_replay(self, snr_db: float, bits: bytes, noise: Optional[np.ndarray], n_symbols: int, *,
+                   compare_limit_bits: int = 0, dump: Optional[tuple] = None):
+        buf = np.frombuffer(bits, dtype=np.uint8) if not isinstance(bits, np.ndarray) else np.ascontiguousarray(bits, dtype=np.uint8)
+        if noise is None:
+            nptr, ndt = None, NOISE_NONE
+        else:
+            noise = np.ascontiguousarray(noise)
+            if noise.dtype == np.complex64:
+                ndt = NOISE_C64
+            elif noise.dtype == np.complex128:
+                ndt = NOISE_C128
+            else:
+                raise ValueError("noise must be complex64 or complex128")
+            if noise.size != n_symbols * (self.n_subcarriers + self.prefix_len):
+                raise ValueError("noise must hold (N + P) samples per OFDM symbol")
+            nptr = noise.ctypes.data
+        d, arrs = self._dump_arrays(n_symbols, dump)
+        res = LinkResult()
+        _check(lib.ofdm_link_run_replay(self._h, snr_db, buf.ctypes.data, buf.size, nptr, ndt, n_symbols,
+                                        compare_limit_bits, None if d is None else C.byref(d), C.byref(res)))
+        out = LinkCounters.from_struct(res)
+        return (out, arrs) if dump else out
+
+    # ---- device-pointer entry points (asynchronous on a CUDA stream handle)
+    def reset_counters(self, stream: int = 0) -> None:
+        _check(lib.ofdm_link_reset_counters(self._h, stream))
+
+    def launch_fused(self, snr_db: float, noise_sigma: float, n_symbols: int, *, seed: int = 0x0FD3, point: int = 0,
+                     first_symbol: int = 0, stream: int = 0) -> None:
+        _check(lib.ofdm_link_launch_fused(self._h, snr_db, noise_sigma, seed, point, first_symbol, n_symbols, None, stream))
+
+    def launch_replay(self, snr_db: float, bits_dev: int, n_bytes: int, noise_dev: int, noise_dtype: int,
+                      n_symbols: int, *, compare_limit_bits: int = 0, stream: int = 0) -> None:
+        _check(lib.ofdm_link_launch_replay(self._h, snr_db, bits_dev, n_bytes, noise_dev, noise_dtype, n_symbols,
+                                           compare_limit_bits, None, stream))
+
+    def read_result(self, stream: int = 0) -> LinkCounters:
+        res = LinkResult()
+        _check(lib.ofdm_link_read_result(self._h, stream, C.byref(res)))
+        return LinkCounters.from_struct(res)
+
+    @property
+    def counters_device_ptr(self) -> int:
+        return int(lib.ofdm_link_counters_device_ptr(self._h) or 0)
+
+
+def measure_fp32_tflops(iters: int = 4096) -> float:
+    require_gpu()
+    return float(lib.ofdm_b200_measure_fp32_tflops(iters))
+
+
+def launch_count() -> int:
+    return int(lib.ofdm_b200_launch_count())

@@ -1,0 +1,106 @@
+"""Fused (Philox) mode on the GPU: the kernel dumps the bits and noise it generated in registers; the
+oracle replays exactly those through the reference algorithm and must arrive at the same decisions
+and error counts.  Plus distribution checks of the in-register generators and shard invariance."""
+import numpy as np
+import pytest
+
+import ofdm_oracle as oc
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, N, order, scheme, channel, prefix, P, eq, snr, modulator, n_ofdm
+    ("headline", 1024, 64, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 20.0, "OFDM", 6),
+    ("c1", 64, 4, "QAM", "flat_fading", "CYCLIC", 16, "ZF", 6.0, "OFDM", 64),
+    ("c2", 1024, 16, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 16.0, "OFDM", 6),
+    ("c5", 4096, 256, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 30.0, "OFDM", 3),
+    ("zp", 256, 16, "QAM", "rayleigh_fading", "ZERO", 5, "MMSE", 15.0, "OFDM", 16),
+    ("isi", 128, 64, "QAM", "severe_multipath", "CYCLIC", 2, "ZF", 24.0, "OFDM", 40),
+    ("none", 64, 16, "QAM", "Lin-Phoong_P2", "NONE", 0, "MMSE", 22.0, "OFDM", 48),
+    ("sc", 512, 4, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "ZF", 8.0, "SC-OFDM", 10),
+    ("psk", 2048, 8, "PSK", "two_ray", "CYCLIC", 1, "MMSE", 15.0, "OFDM", 4),
+    ("n8192", 8192, 16, "QAM", "default_multipath", "CYCLIC", 3, "MMSE", 18.0, "OFDM", 2),
+    ("n16", 16, 4, "QAM", "two_ray", "CYCLIC", 1, "ZF", 10.0, "OFDM", 200),
+    ("n32", 32, 16, "QAM", "two_ray", "ZERO", 1, "MMSE", 18.0, "OFDM", 100),
+    ("n8", 8, 4, "PSK", "flat_fading", "NONE", 0, "NONE", 8.0, "OFDM", 300),
+]
+
+
+def pack_labels(labels, bps_per_sc):
+    """labels[S, N] -> the byte stream the reference's encode() would have consumed."""
+    bits = []
+    for k, b in enumerate(bps_per_sc):
+        if b:
+            sh = np.arange(b - 1, -1, -1)
+            bits.append(((labels[:, k, None].astype(np.int64) >> sh) & 1))
+    return oc.pack_bits(np.concatenate(bits, axis=1).reshape(-1))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fused_dump_replays_through_oracle(case, kat):
+    from ofdm_based_systems._native import Link
+    name, n, order, scheme, chan, prefix, P, eq, snr, modulator, n_ofdm = case
+    taps_raw = kat["chan_" + chan]
+    setup = oc.LinkSetup(n_sc=n, taps_raw=taps_raw, snr_db=snr, order=order, scheme=scheme, modulator=modulator,
+                         prefix_type=prefix, eq=eq, prefix_len_override=P)
+    sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
+    link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
+                modulator=modulator, equalizer=eq, scheme=scheme)
+    res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=1000 if name != "isi" else 0,
+                            dump=("z", "rx_labels", "tx_labels", "noise"))
+    bps = oc.bits_per_symbol(order)
+    tx_bytes = pack_labels(d["tx_labels"], [bps] * n)
+    ref = oc.run_link(setup, tx_bytes, n_ofdm * n * bps, noise=d["noise"].astype(np.complex128).reshape(-1))
+    z_ref = np.asarray(ref["received_symbols"]).reshape(n_ofdm, n)
+    assert np.max(np.abs(d["z"] - z_ref)) / np.max(np.abs(z_ref)) < 1e-5
+    f = oc.qam_boundary_distance if scheme == "QAM" else oc.psk_boundary_distance
+    mismatch = d["rx_labels"] != np.asarray(ref["rx_labels"]).reshape(n_ofdm, n)
+    assert not np.any(mismatch & (f(z_ref, order) > 2e-4))
+    if not mismatch.any():
+        assert res.bit_errors == ref["bit_errors"]
+        assert res.symbol_errors == ref["symbol_errors"]
+    assert res.bits == n_ofdm * n * bps
+    assert abs(res.papr_db - ref["papr_db"]) < 2e-4
+    link.close()
+
+
+def test_generators_are_well_distributed(kat):
+    from ofdm_based_systems._native import Link
+    n, n_ofdm = 1024, 64
+    taps = oc.normalize_taps(kat["chan_severe_multipath"])
+    link = Link(n, taps, np.fft.fft(taps, n), np.full(n, 64), prefix_type="CYCLIC", prefix_len=7)
+    _, d = link.run_fused(10.0, 0.5, n_ofdm, seed=7, dump=("tx_labels", "noise"))
+    w = d["noise"][:, 7:].reshape(-1).astype(np.complex128)      # the prefix samples are never generated
+    m = w.size
+    assert abs(w.real.mean()) < 5 * 0.5 / np.sqrt(m) and abs(w.imag.mean()) < 5 * 0.5 / np.sqrt(m)
+    assert abs(w.real.var() / 0.25 - 1) < 0.02 and abs(w.imag.var() / 0.25 - 1) < 0.02
+    assert abs(np.mean(w.real * w.imag)) < 5 * 0.25 / np.sqrt(m)
+    kurt = np.mean(w.real ** 4) / w.real.var() ** 2
+    assert abs(kurt - 3) < 0.1
+    assert np.all(d["noise"][:, :7] == 0)
+    counts = np.bincount(d["tx_labels"].reshape(-1), minlength=64)
+    expected = n * n_ofdm / 64
+    assert np.all(np.abs(counts - expected) < 6 * np.sqrt(expected))
+    link.close()
+
+
+def test_sharding_is_invariant(kat):
+    """Counters of [0, S) equal the sum over any partition of the symbol range."""
+    from ofdm_based_systems._native import Link
+    n = 256
+    taps = oc.normalize_taps(kat["chan_severe_multipath"])
+    for prefix, P in (("CYCLIC", 7), ("CYCLIC", 2), ("ZERO", 3), ("NONE", 0)):
+        link = Link(n, taps, np.fft.fft(taps, n), np.full(n, 16), prefix_type=prefix, prefix_len=P)
+        sigma = float(np.sqrt(1 / 10 ** 1.4 / 2))
+        whole = link.run_fused(14.0, sigma, 900, seed=99, point=1)
+        parts = [link.run_fused(14.0, sigma, cnt, seed=99, point=1, first_symbol=start)
+                 for start, cnt in ((0, 301), (301, 299), (600, 300))]
+        assert whole.bit_errors == sum(p.bit_errors for p in parts) and whole.bit_errors > 0
+        assert whole.symbol_errors == sum(p.symbol_errors for p in parts)
+        assert whole.bits == sum(p.bits for p in parts)
+        assert whole.tx_power_max == max(p.tx_power_max for p in parts)
+        assert abs(whole.tx_power_sum - sum(p.tx_power_sum for p in parts)) < 1e-6 * whole.tx_power_sum
+        other = link.run_fused(14.0, sigma, 900, seed=100, point=1)
+        assert other.bit_errors != whole.bit_errors
+        link.close()
