@@ -78,6 +78,8 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
                      const int32_t* orders, const double* amp, ofdm_link** out);
 void ofdm_link_destroy(ofdm_link* link);
 int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* link);
+/* bytes ofdm_link_create copied host -> device for this link (tables; bench.py's h2d accounting) */
+uint64_t ofdm_link_table_bytes(const ofdm_link* link);
 
 /* Fused Monte-Carlo mode: replaces simulation/models.py:454-606 for OFDM symbols
  * [first_symbol, first_symbol + n_symbols) of SNR point `point`; bits and AWGN come from

@@ -283,6 +283,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   CUDA_TRY(cudaMemcpy(L->d_eq, eq.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(L->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(L->d_cnt, 0, sizeof(CounterBlock)));
+  L->table_bytes = 2 * size_t(N) * sizeof(float4) + tw.size() * sizeof(float2);
   *out = L;
   return OFDM_OK;
 }
@@ -298,6 +299,7 @@ void ofdm_link_destroy(ofdm_link* L) {
 }
 
 int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* L) { return L ? L->bits_per_ofdm : OFDM_EINVAL; }
+uint64_t ofdm_link_table_bytes(const ofdm_link* L) { return L ? L->table_bytes : 0; }
 void* ofdm_link_counters_device_ptr(ofdm_link* L) { return L ? (void*)L->d_cnt : nullptr; }
 
 int ofdm_link_reset_counters(ofdm_link* L, void* stream) {

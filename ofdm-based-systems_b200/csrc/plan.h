@@ -44,6 +44,7 @@ struct ofdm_link {
   ofdm::CounterBlock* d_cnt = nullptr;
   int device = 0, sms = 0, occ = 1;
   size_t smem = 0;
+  size_t table_bytes = 0;
 };
 
 namespace ofdm {

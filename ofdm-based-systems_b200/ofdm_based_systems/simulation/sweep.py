@@ -1,0 +1,165 @@
+"""Sharded BER-vs-SNR sweeps on top of the CUDA link (libofdm_b200.so).
+
+The reference loops over SNR points strictly sequentially, one ``Simulation.run()`` each
+(main.py:234-240).  Here one ``LinkSweep`` owns one configured link per GPU; every SNR point is one
+kernel launch over this rank's contiguous share of the OFDM-symbol range, all launches are queued on
+one CUDA stream, and the per-rank counters of ALL points are combined by a single NCCL all-reduce at
+the end of the sweep.  torch is used for the stream, the device tensors that hold the
+counters and ``torch.distributed``; the arithmetic is in the CUDA library.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from ofdm_based_systems import _native
+
+
+@dataclass
+class LinkConfig:
+    """What ``Simulation.run()`` fixes before its hot loop (simulation/models.py:226-410)."""
+    num_subcarriers: int
+    taps_raw: np.ndarray                      # as loaded from the .npy / the 4-tap default (NOT normalised)
+    constellation_order: int = 16
+    constellation_scheme: str = "QAM"
+    modulator_type: str = "OFDM"
+    prefix_scheme: str = "CYCLIC"
+    prefix_length: int = 0
+    equalizator_type: str = "MMSE"
+    awgn: bool = True
+    orders: Optional[np.ndarray] = None      # adaptive mode: per-subcarrier orders
+    amp: Optional[np.ndarray] = None         # optional per-subcarrier tx amplitude (sqrt of allocated power)
+    taps_chan: np.ndarray = field(init=False)
+    h_eq: np.ndarray = field(init=False)
+
+    def __post_init__(self):
+        self.taps_raw = np.asarray(self.taps_raw, dtype=np.complex128)
+        power = np.sum(np.abs(self.taps_raw) ** 2)
+        if power == 0:
+            raise ValueError("Impulse response cannot be all zeros.")          # channel/models.py:43
+        self.taps_chan = self.taps_raw / np.sqrt(power)                        # channel/models.py:14-16
+        self.h_eq = np.fft.fft(self.taps_raw, self.num_subcarriers)            # simulation/models.py:263-266
+        if self.orders is None:
+            self.orders = np.full(self.num_subcarriers, self.constellation_order, dtype=np.int64)
+        self.orders = np.asarray(self.orders, dtype=np.int64)
+
+    @property
+    def bits_per_ofdm_symbol(self) -> int:
+        return int(sum(int(np.log2(o)) for o in self.orders if o > 1))
+
+    def stream_power(self) -> float:
+        """Analytic mean |.|^2 of the serial stream after the channel, the quantity AWGNoiseModel
+        measures (noise/models.py:14).  With unit-power constellations on the active subcarriers the
+        in-symbol sample power is (1/N) sum_k a_k |H_k|^2 (H from the normalised taps); a zero-padded
+        stream spreads one symbol's energy over N + P samples."""
+        n = self.num_subcarriers
+        a = (self.orders > 1).astype(np.float64)
+        if self.amp is not None:
+            a = a * np.asarray(self.amp, dtype=np.float64) ** 2
+        if self.modulator_type == "OFDM":
+            p = float(np.mean(a * np.abs(np.fft.fft(self.taps_chan, n)) ** 2))
+        else:  # SC-OFDM: the constellation symbols are the time samples (white)
+            p = float(np.mean(a) * np.sum(np.abs(self.taps_chan) ** 2))
+        if self.prefix_scheme == "ZERO":
+            p *= n / (n + self.prefix_length)
+        return p
+
+    def noise_sigma(self, snr_db: float) -> float:
+        """Per-component standard deviation sqrt(P / snr_lin / 2) (noise/models.py:15-20)."""
+        if not self.awgn:
+            return 0.0
+        return float(np.sqrt(self.stream_power() / (10 ** (snr_db / 10)) / 2))
+
+
+class _DeviceWords:
+    """Zero-copy torch view of device memory owned by the CUDA library."""
+
+    def __init__(self, ptr: int, n_words: int):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+N_WORDS = 10  # 8 x uint64 counters, double power sum, uint64 bits of the double power max
+
+
+class LinkSweep:
+    def __init__(self, cfg: LinkConfig, device: Optional[int] = None):
+        self.cfg = cfg
+        self.link = _native.Link(cfg.num_subcarriers, cfg.taps_chan, cfg.h_eq, cfg.orders,
+                                 prefix_type=cfg.prefix_scheme, prefix_len=cfg.prefix_length,
+                                 modulator=cfg.modulator_type, equalizer=cfg.equalizator_type,
+                                 scheme=cfg.constellation_scheme, amp=cfg.amp, device=-1 if device is None else device)
+        self.device = device
+
+    def close(self):
+        self.link.close()
+
+    # ---- one rank, one point, synchronous (host result): the plain C-ABI call
+    def run_point(self, snr_db: float, n_symbols: int, *, seed: int = 0x0FD3, point: int = 0, first_symbol: int = 0):
+        return self.link.run_fused(snr_db, self.cfg.noise_sigma(snr_db), n_symbols, seed=seed, point=point,
+                                   first_symbol=first_symbol)
+
+    # ---- whole sweep, sharded over the ranks of a torch.distributed group
+    @staticmethod
+    def shard(n_symbols: int, rank: int, world: int):
+        """Contiguous share [first, first + count) of the symbol range (contiguity keeps the
+        inter-symbol-interference chain intact inside a shard)."""
+        base, rem = divmod(n_symbols, world)
+        first = rank * base + min(rank, rem)
+        return first, base + (1 if rank < rem else 0)
+
+    def enqueue(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
+                weak_scaling: bool = False):
+        """Queue every SNR point on the current CUDA stream, then ONE all-reduce; nothing is read back.
+        Returns the device tensor [points, 9 + world] (float64) that ``finalize`` decodes."""
+        import torch
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank(group) if distributed else 0
+        world = dist.get_world_size(group) if distributed else 1
+        if weak_scaling:
+            first, count = rank * n_symbols, n_symbols
+        else:
+            first, count = self.shard(n_symbols, rank, world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        stream = torch.cuda.current_stream().cuda_stream
+        block = torch.as_tensor(_DeviceWords(self.link.counters_device_ptr, N_WORDS), device=dev)
+        k = len(snr_dbs)
+        rows = torch.empty((k, N_WORDS), dtype=torch.int64, device=dev)
+        for i, snr in enumerate(snr_dbs):
+            block.zero_()
+            self.link.launch_fused(float(snr), self.cfg.noise_sigma(float(snr)), count, seed=seed, point=i,
+                                   first_symbol=first, stream=stream)
+            rows[i].copy_(block)
+        # one SUM all-reduce carries the counters, the power sums and (one slot per rank) the maxima
+        payload = torch.zeros((k, 9 + world), dtype=torch.float64, device=dev)
+        payload[:, :8] = rows[:, :8].to(torch.float64)           # counts < 2^53 are exact in float64
+        payload[:, 8] = rows[:, 8].view(torch.float64)
+        payload[:, 9 + rank] = rows[:, 9].view(torch.float64)
+        if distributed and world > 1:
+            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+        return payload
+
+    def finalize(self, snr_dbs: Sequence[float], payload) -> List[dict]:
+        """Device -> host read of the combined counters; result keys follow the reference's result dict
+        (bit_errors / total_bits / bit_error_rate / symbol_errors / symbol_error_rate / papr_db)."""
+        host = payload.cpu().numpy()
+        n_pre = self.cfg.num_subcarriers + self.cfg.prefix_length
+        out = []
+        for i, snr in enumerate(snr_dbs):
+            c = host[i]
+            bit_errors, bits, sym_errors, syms, ofdm = (int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]))
+            mean_p = c[8] / max(ofdm * n_pre, 1)
+            out.append(dict(snr_db=float(snr), bit_errors=bit_errors, total_bits=bits, symbol_errors=sym_errors,
+                            num_constellation_symbols=syms, num_ofdm_symbols=ofdm,
+                            bit_error_rate=bit_errors / bits if bits else 0.0,
+                            symbol_error_rate=sym_errors / syms if syms else 0.0,
+                            papr_db=float(10 * np.log10(c[9:].max() / mean_p)) if mean_p > 0 else float("inf")))
+        return out
+
+    def sweep(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
+              weak_scaling: bool = False) -> List[dict]:
+        """``n_symbols`` is the global OFDM-symbol count per point (the per-rank count with
+        ``weak_scaling``); the symbol range is sharded over the ranks of the process group."""
+        return self.finalize(snr_dbs, self.enqueue(snr_dbs, n_symbols, seed=seed, group=group, weak_scaling=weak_scaling))
