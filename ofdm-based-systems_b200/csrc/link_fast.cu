@@ -1,0 +1,40 @@
+// Instantiations + launch glue of the fast-path kernel (link_fast.cuh).
+#include "link_fast.cuh"
+#include "plan.h"
+
+namespace ofdm {
+
+template <int E, bool DUMP>
+static int launch_fast_e(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
+  using G = FastGeometry<E>;
+  auto kern = ofdm_link_fast_kernel<E, DUMP, true>;
+  static int occ_cache[2] = {0, 0};
+  int& occ = occ_cache[DUMP ? 1 : 0];
+  if (occ == 0) {
+    if (G::SMEM_BYTES > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::BLOCK, G::SMEM_BYTES));
+    if (occ <= 0) occ = 1;
+  }
+  const unsigned long long need = (p.sym_count + G::TEAMS - 1) / G::TEAMS;
+  unsigned long long grid = (unsigned long long)L->sms * occ;
+  if (need < grid) grid = need;
+  if (grid == 0) return OFDM_OK;
+  kern<<<(unsigned)grid, G::BLOCK, G::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  CUDA_TRY(cudaGetLastError());
+  return OFDM_OK;
+}
+
+bool fast_supports_n(int n) { return n == 64 || n == 256 || n == 1024; }
+
+int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, cudaStream_t stream) {
+  switch (L->d.n_subcarriers) {
+    case 64: return dump ? launch_fast_e<8, true>(L, p, stream) : launch_fast_e<8, false>(L, p, stream);
+    case 256: return dump ? launch_fast_e<16, true>(L, p, stream) : launch_fast_e<16, false>(L, p, stream);
+    case 1024: return dump ? launch_fast_e<32, true>(L, p, stream) : launch_fast_e<32, false>(L, p, stream);
+    default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", L->d.n_subcarriers);
+  }
+}
+
+}  // namespace ofdm

@@ -1,0 +1,368 @@
+// ofdm_link_fast kernel: the Monte-Carlo hot loop for the common link shape
+//   OFDM modulator, square QAM of one order on every subcarrier (4 .. 256), cyclic prefix at least as long
+//   as the channel memory (no inter-symbol interference), <= 8 taps, Philox bits and noise,
+//   N = E*E subcarriers with E in {8, 16, 32}  (N = 64, 256, 1024).
+// Same chain and same reference lines as link_kernel.cuh; what differs is the machine mapping:
+//   * a team of E lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers,
+//   * the instruction working set is kept inside the instruction cache: ONE forward-FFT body serves both
+//     transforms (the IFFT runs as FFT on re/im-swapped data), the FIR + AWGN stage is a rolled loop over
+//     8-sample chunks that works in place in shared memory,
+//   * all scale factors (1/sqrt(2(M-1)/3), the two 1/sqrt(N), the slicer's k/2) are folded on the host into
+//     the FIR taps and the equaliser table, level <-> index conversions use mantissa tricks (no I2F/F2I),
+//   * bit errors are counted on packed words: gray^-1 is linear over GF(2), so the error pattern of a
+//     subcarrier is gray^-1(col_tx ^ col_rx), evaluated four subcarriers per 32-bit word.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fft_regs.cuh"
+#include "link_params.h"
+#include "philox.cuh"
+
+namespace ofdm {
+
+constexpr int kFastTaps = 8;
+
+struct FastParams {
+  float2 taps[kFastTaps];   // unit-energy taps * 1 / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1))
+  const float4* eq_tab;     // MMSE {Re H", Im H", |H|^2, -} with H" = H k / (2 sqrt N); ZF {Re g, Im g, -, -}
+  const float2* tw;         // pass-2 twiddles exp(-2 pi i t r / N) at [(r-1)*E + t]
+  float sigma;              // per-component noise standard deviation
+  float mmse_c;             // sigma2_eq = mmse_c * sum_k |Y~_k|^2   (Y~ = unscaled FFT output)
+  float slice_off;          // (s-1)/2
+  float slice_top;          // s-1
+  float tx_scale2;          // |tx|^2 = tx_scale2 * |x~|^2 (PAPR statistics)
+  float z_unscale;          // DUMP only: Z = (t - slice_off) * z_unscale  (= 2 / k)
+  float noeq_scale;         // equaliser NONE: t = Re(Y~) * noeq_scale + slice_off  (= k / (2 sqrt N))
+  int prefix_len;
+  int equalizer;
+  int half_bits;            // log2(s)
+  unsigned int field_mask;  // (s-1) << 1 replicated in every byte
+  unsigned long long seed;
+  unsigned int point;
+  unsigned long long sym_begin, sym_count;
+  unsigned long long* counters;
+  double* tx_power_sum;
+  unsigned long long* tx_power_max_bits;
+  float2* dump_z;
+  unsigned short* dump_rx;
+  unsigned short* dump_tx;
+  float2* dump_noise;
+};
+
+template <int E>
+struct FastGeometry {
+  static constexpr int N = E * E;
+  static constexpr int T = E;                 // lanes per OFDM symbol
+  static constexpr int RS = E + 2;            // row stride (complex): conflict-free 128-bit row accesses
+  static constexpr int TEAM_F2 = E * RS;      // float2 per team
+  static constexpr int BLOCK = 128;
+  static constexpr int TEAMS = BLOCK / T;
+  static constexpr size_t SMEM_BYTES = size_t(TEAMS) * TEAM_F2 * sizeof(float2);
+};
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// circularly-symmetric N(0,1)+jN(0,1) from two 32-bit words (same distribution as box_muller())
+__device__ __forceinline__ float2 fast_box_muller(uint32_t wr, uint32_t wa, float sigma) {
+  const float u1 = fmaf((float)wr, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float rad = sigma * fast_sqrt(-1.3862943611198906f * fast_lg2(u1));  // sqrt(-2 ln u)
+  const float ang = (float)(int32_t)wa * 1.4629180792671596e-09f;            // (-pi, pi)
+  return make_float2(rad * __cosf(ang), rad * __sinf(ang));
+}
+
+// prefix-XOR inside the 4-bit fields that sit at bits 1..4 / 5..8 of every byte (inverse Gray code)
+__device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
+  x ^= x >> 1;
+  x ^= x >> 2;
+  return x;
+}
+
+template <int E, bool DUMP, bool PAPR>
+__global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+  using G = FastGeometry<E>;
+  constexpr int N = G::N, T = G::T, RS = G::RS, WORDS = E / 4;
+  constexpr int CALLS = (E + 15) / 16;  // Philox calls for E random bytes
+  extern __shared__ float4 smem4[];
+  const int lane = threadIdx.x & 31;
+  const int t = lane % T;
+  const int team_in_block = threadIdx.x / T;
+  float2* buf = reinterpret_cast<float2*>(smem4) + size_t(team_in_block) * G::TEAM_F2;
+  float2* row = buf + t * RS;
+
+  const unsigned long long n_teams = (unsigned long long)gridDim.x * G::TEAMS;
+  const unsigned long long team_id = (unsigned long long)blockIdx.x * G::TEAMS + team_in_block;
+  const unsigned long long iters = (p.sym_count + n_teams - 1) / n_teams;
+  const PhiloxKey key{(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
+  const int P = p.prefix_len;
+  const float magic = 8388608.0f;  // 2^23
+
+  unsigned long long acc_bit_err = 0, acc_sym_err = 0, acc_syms = 0;
+  double acc_pow = 0.0;
+  float acc_max = 0.f;
+
+  for (unsigned long long it = 0; it < iters; ++it) {
+    const unsigned long long s = it * n_teams + team_id;
+    const bool active = s < p.sym_count;
+    const unsigned long long gs = p.sym_begin + (active ? s : 0ull);
+    const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
+
+    unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1.. of each byte
+    float2 v[E];
+
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 0) {
+        // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
+        //      low nibble -> column (in-phase) index, high nibble -> row (quadrature) index.
+#pragma unroll
+        for (int c = 0; c < CALLS; ++c) {
+          const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), p.point), key);
+          const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * c + j < WORDS) {
+              txc[4 * c + j] = (ww[j] << 1) & p.field_mask;   // bits 0..3 of each byte -> column index
+              txr[4 * c + j] = (ww[j] >> 3) & p.field_mask;   // bits 4..7 of each byte -> row index
+            }
+          }
+        }
+        // level = 2*index - (s-1) as float via the mantissa of 2^23 + (2*index + 1); re/im swapped so the
+        // forward FFT below computes the inverse transform
+        const float cen = -(magic + p.slice_top + 1.0f);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const unsigned fc = __byte_perm(txc[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
+          const unsigned fr = __byte_perm(txr[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
+          const float li = __uint_as_float(fc) + cen;        // I level:  2*col - (s-1)
+          const float lq = -(__uint_as_float(fr) + cen);     // Q level: (s-1) - 2*row
+          v[m] = make_float2(lq, li);
+        }
+      } else {
+        // ---- channel + noise, in place in shared memory, 8 samples per iteration
+        //      (channel/models.py:52-55 restricted to P >= L-1 -> circular; noise/models.py:19-22)
+        float2 prev[8];
+        {
+          const float2* hrow = buf + ((t + T - 1) % T) * RS + (E - 8);
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 q = *reinterpret_cast<const float4*>(hrow + i);
+            prev[i] = make_float2(q.x, q.y);
+            prev[i + 1] = make_float2(q.z, q.w);
+          }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < E / 8; ++c) {
+          float2 cur[8], y[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float4 q = *reinterpret_cast<const float4*>(row + 8 * c + i);
+            cur[i] = make_float2(q.x, q.y);
+            cur[i + 1] = make_float2(q.z, q.w);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float yr = 0.f, yi = 0.f;
+#pragma unroll
+            for (int l = 0; l < kFastTaps; ++l) {
+              const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
+              const float2 h = p.taps[l];
+              yr = fmaf(h.x, x.x, yr);
+              yr = fmaf(-h.y, x.y, yr);
+              yi = fmaf(h.x, x.y, yi);
+              yi = fmaf(h.y, x.x, yi);
+            }
+            y[i] = make_float2(yr, yi);
+          }
+          if (p.sigma > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t pair = uint32_t((E * t + 8 * c) >> 1) + j;
+              const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (1u << 28) | pair, p.point), key);
+              const float2 g0 = fast_box_muller(w.x, w.y, p.sigma), g1 = fast_box_muller(w.z, w.w, p.sigma);
+              if (DUMP) {
+                if (active && p.dump_noise) {
+                  float2* dn = p.dump_noise + s * (unsigned long long)(N + P) + P + E * t + 8 * c + 2 * j;
+                  dn[0] = g0;
+                  dn[1] = g1;
+                }
+              }
+              y[2 * j] = cadd(y[2 * j], g0);
+              y[2 * j + 1] = cadd(y[2 * j + 1], g1);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i += 2)
+            *reinterpret_cast<float4*>(row + 8 * c + i) = make_float4(y[i].x, y[i].y, y[i + 1].x, y[i + 1].y);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) prev[i] = cur[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = buf[m * RS + t];
+        __syncwarp();
+      }
+
+      // ---- forward FFT of N = E*E points: radix-E in registers, row/column exchange, twiddle, radix-E
+      fft_dif_inplace<E, -1>(v);
+#pragma unroll
+      for (int r = 0; r < E; r += 2) {
+        const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
+        *reinterpret_cast<float4*>(row + r) = make_float4(a.x, a.y, b.x, b.y);
+      }
+      __syncwarp();
+      float2 u[E];
+#pragma unroll
+      for (int m = 0; m < E; ++m) u[m] = buf[m * RS + t];
+      __syncwarp();
+#pragma unroll
+      for (int r = 1; r < E; ++r) u[r] = cmul(u[r], __ldg(&p.tw[(r - 1) * T + t]));
+      fft_dif_inplace<E, -1>(u);
+
+      if (phase == 0) {
+        // ---- x~[t + T m] = swap(u[brev m]); PAPR statistics; publish for the FIR (prefix/models.py:34-44)
+        float ssum = 0.f, smax = 0.f;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float2 o = u[fft_out_index<E>(m)];
+          const float2 x = make_float2(o.y, o.x);
+          if (PAPR) {
+            const float pw = fmaf(x.x, x.x, x.y * x.y);
+            const int n = t + T * m;
+            ssum += (n >= N - P) ? 2.f * pw : pw;   // the cyclic prefix repeats the last P samples
+            smax = fmaxf(smax, pw);
+          }
+          buf[m * RS + t] = x;
+        }
+        if (PAPR && active) {
+          acc_pow += double(ssum);
+          acc_max = fmaxf(acc_max, smax);
+        }
+        __syncwarp();
+      } else {
+        // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
+        //      simulation/models.py:597-606)
+        float sigma2 = 0.f;
+        if (p.equalizer == EQ_MMSE) {
+          float ss = 0.f;
+#pragma unroll
+          for (int m = 0; m < E; ++m) ss = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, ss));
+#pragma unroll
+          for (int off = T / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+          sigma2 = ss * p.mmse_c;
+        }
+        unsigned rxc[WORDS], rxr[WORDS];
+#pragma unroll
+        for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float2 yv = u[fft_out_index<E>(m)];
+          const int k = t + T * m;
+          float tc, tr;
+          if (p.equalizer == EQ_NONE) {
+            tc = fmaf(yv.x, p.noeq_scale, p.slice_off);
+            tr = fmaf(-yv.y, p.noeq_scale, p.slice_off);
+          } else {
+            const float4 e = __ldg(&p.eq_tab[k]);
+            float a, b, inv = 1.f;
+            if (p.equalizer == EQ_MMSE) {
+              a = fmaf(yv.x, e.x, yv.y * e.y);          // Re(Y conj H")
+              b = fmaf(yv.x, e.y, -yv.y * e.x);         // -Im(Y conj H")
+              inv = fast_rcp(e.z + sigma2);
+            } else {
+              a = fmaf(yv.x, e.x, -yv.y * e.y);         // Re(Y g)
+              b = -fmaf(yv.x, e.y, yv.y * e.x);         // -Im(Y g)
+            }
+            tc = fmaf(a, inv, p.slice_off);
+            tr = fmaf(b, inv, p.slice_off);
+          }
+          if (DUMP) {
+            if (active && p.dump_z)
+              p.dump_z[s * N + k] = make_float2((tc - p.slice_off) * p.z_unscale, (p.slice_off - tr) * p.z_unscale);
+          }
+          tc = fminf(fmaxf(tc, 0.f), p.slice_top) + magic;   // low mantissa bits = rint(clamped)
+          tr = fminf(fmaxf(tr, 0.f), p.slice_top) + magic;
+          // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
+          rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
+          rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
+        }
+        unsigned be = 0, se = 0;
+#pragma unroll
+        for (int j = 0; j < WORDS; ++j) {
+          // sum over the 4 bytes of (0x4B000000 << (8i+1)) mod 2^32: only i = 0 survives
+          constexpr unsigned K = (0x4B000000u << 1);
+          const unsigned dc = ((rxc[j] - K) ^ txc[j]) & 0x1E1E1E1Eu;
+          const unsigned dr = ((rxr[j] - K) ^ txr[j]) & 0x1E1E1E1Eu;
+          be += __popc(inv_gray_fields(dc) & 0x1E1E1E1Eu) + __popc(inv_gray_fields(dr) & 0x1E1E1E1Eu);
+          unsigned any = dc | dr;
+          any |= any >> 2;
+          any |= any >> 1;
+          se += __popc(any & 0x02020202u);
+          if (DUMP) {
+            if (active) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int m = 4 * j + i, k = t + T * m;
+                const unsigned ct = (txc[j] >> (8 * i + 1)) & 15u, rt = (txr[j] >> (8 * i + 1)) & 15u;
+                const unsigned cr = ((rxc[j] - K) >> (8 * i + 1)) & 15u, rr = ((rxr[j] - K) >> (8 * i + 1)) & 15u;
+                auto ig = [](unsigned x) { x ^= x >> 1; x ^= x >> 2; return x & 15u; };
+                if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((ig(rt) << p.half_bits) | ig(ct));
+                if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rr) << p.half_bits) | ig(cr));
+              }
+            }
+          }
+        }
+        if (active) {
+          acc_bit_err += be;
+          acc_sym_err += se;
+          acc_syms += E;
+        }
+      }
+    }
+  }
+
+  // ---- counters: warp shuffle, one atomic per warp
+  auto warp_sum64 = [](unsigned long long x) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    return x;
+  };
+  const unsigned long long b0 = warp_sum64(acc_bit_err), b2 = warp_sum64(acc_sym_err), b3 = warp_sum64(acc_syms);
+  double pw = acc_pow;
+  float mx = acc_max;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    pw += __shfl_down_sync(0xffffffffu, pw, off);
+    mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, off));
+  }
+  if (lane == 0) {
+    if (b0) atomicAdd(&p.counters[CNT_BIT_ERRORS], b0);
+    if (b3) {
+      atomicAdd(&p.counters[CNT_BITS], b3 * (unsigned long long)(2 * p.half_bits));
+      atomicAdd(&p.counters[CNT_SYMBOLS], b3);
+      atomicAdd(&p.counters[CNT_OFDM_SYMBOLS], b3 / N);
+    }
+    if (b2) atomicAdd(&p.counters[CNT_SYM_ERRORS], b2);
+    if (PAPR) {
+      atomicAdd(p.tx_power_sum, pw * double(p.tx_scale2));
+      atomicMax(p.tx_power_max_bits, (unsigned long long)__double_as_longlong(double(mx) * double(p.tx_scale2)));
+    }
+  }
+}
+
+}  // namespace ofdm

@@ -10,6 +10,9 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
+#include "link_fast.cuh"
 #include "plan.h"
 
 using namespace ofdm;
@@ -268,6 +271,40 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   L->bits_per_ofdm = bit_off;
   L->mean_h2 = sum_h2 / N;
 
+  // ---- fast-path eligibility (link_fast.cuh) and its folded tables
+  {
+    bool uniform = true;
+    for (int k = 1; k < N; ++k) uniform = uniform && (orders[k] == orders[0]);
+    const int M = orders[0];
+    const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
+    L->fast = uniform && !amp && (M == 4 || M == 16 || M == 64 || M == 256) && desc->scheme == OFDM_SCHEME_QAM &&
+              desc->modulator == OFDM_MOD_OFDM && desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 &&
+              Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1');
+    if (L->fast) {
+      L->fixed_order = M;
+      const double knorm = std::sqrt(2.0 * (M - 1) / 3.0), sqn = std::sqrt((double)N);
+      L->knorm = knorm;
+      const double tap_scale = 1.0 / (knorm * sqn);   // levels are 2c-(s-1) = k * point; unnormalised IFFT
+      for (int l = 0; l < kFastTaps; ++l)
+        L->taps_fast[l] = l < Lt ? make_float2((float)(taps_chan[2 * l] * tap_scale), (float)(taps_chan[2 * l + 1] * tap_scale))
+                                 : make_float2(0.f, 0.f);
+      const double dec = knorm / (2.0 * sqn);               // slicer scale k/2 and the receiver's 1/sqrt(N)
+      std::vector<float4> eqf(N);
+      for (int k = 0; k < N; ++k) {
+        const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
+        if (desc->equalizer == OFDM_EQ_ZF) {
+          const std::complex<double> h = (H == std::complex<double>(0.0, 0.0)) ? std::complex<double>(1e-10, 0.0) : H;
+          const std::complex<double> g = dec / h;
+          eqf[k] = make_float4((float)g.real(), (float)g.imag(), 0.f, 0.f);
+        } else {
+          eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), 0.f);
+        }
+      }
+      CUDA_TRY(cudaMalloc(&L->d_eq_fast, N * sizeof(float4)));
+      CUDA_TRY(cudaMemcpy(L->d_eq_fast, eqf.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+  }
+
   int rc = configure(L);
   if (rc != OFDM_OK) { delete L; return rc; }
   cudaDeviceProp prop;
@@ -295,6 +332,7 @@ void ofdm_link_destroy(ofdm_link* L) {
   cudaFree(L->d_eq);
   cudaFree(L->d_tw);
   cudaFree(L->d_cnt);
+  cudaFree(L->d_eq_fast);
   delete L;
 }
 
@@ -320,6 +358,45 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
   if (!L) return fail(OFDM_EINVAL, "null link");
   if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
   DeviceGuard guard(L->device);
+  if (L->fast && !(dump_dev && dump_dev->y)) {
+    // common link shape: the fast kernel (link_fast.cuh); its Philox streams are its own
+    const int N = L->d.n_subcarriers, M = L->fixed_order;
+    int half_bits = 0;
+    while ((1 << (2 * half_bits)) < M) ++half_bits;
+    const int side = 1 << half_bits;
+    FastParams f;
+    std::memset(&f, 0, sizeof(f));
+    std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
+    f.eq_tab = L->d_eq_fast;
+    f.tw = L->d_tw;
+    f.sigma = (float)noise_sigma;
+    const double snr_lin = std::pow(10.0, snr_db / 10.0);
+    f.mmse_c = L->mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
+    f.slice_off = 0.5f * float(side - 1);
+    f.slice_top = float(side - 1);
+    const double tap_scale = 1.0 / (L->knorm * std::sqrt((double)N));
+    f.tx_scale2 = (float)(tap_scale * tap_scale);
+    f.z_unscale = (float)(2.0 / L->knorm);
+    f.noeq_scale = (float)(L->knorm / (2.0 * std::sqrt((double)N)));
+    f.prefix_len = L->d.prefix_len;
+    f.equalizer = L->d.equalizer;
+    f.half_bits = half_bits;
+    f.field_mask = 0x01010101u * (unsigned)((side - 1) << 1);
+    f.seed = seed;
+    f.point = point;
+    f.sym_begin = first_symbol;
+    f.sym_count = n_symbols;
+    f.counters = L->d_cnt->cnt;
+    f.tx_power_sum = &L->d_cnt->power_sum;
+    f.tx_power_max_bits = &L->d_cnt->power_max_bits;
+    if (dump_dev) {
+      f.dump_z = reinterpret_cast<float2*>(dump_dev->z);
+      f.dump_rx = dump_dev->rx_labels;
+      f.dump_tx = dump_dev->tx_labels;
+      f.dump_noise = reinterpret_cast<float2*>(dump_dev->noise);
+    }
+    return launch_fast(L, f, dump_dev != nullptr, (cudaStream_t)stream);
+  }
   LinkParams p;
   fill_params(L, p, snr_db);
   p.bits_src = SRC_PHILOX;

@@ -45,12 +45,24 @@ struct ofdm_link {
   int device = 0, sms = 0, occ = 1;
   size_t smem = 0;
   size_t table_bytes = 0;
+  // fast path (link_fast.cuh): eligible link shapes only
+  int fast = 0;                 // 1 if the fast kernel can run this link in fused mode
+  int fixed_order = 0;          // the single QAM order when fast
+  float4* d_eq_fast = nullptr;  // decision-domain equaliser table
+  float2 taps_fast[8];
+  double knorm = 1.0;
 };
 
 namespace ofdm {
 // defined in link_inst.cu, one explicit instantiation per supported size
 template <int N> int configure_kernel(ofdm_link* L);
 template <int N> int launch_kernel(const ofdm_link* L, const LinkParams& p, cudaStream_t stream);
+}  // namespace ofdm
+
+namespace ofdm {
+struct FastParams;
+bool fast_supports_n(int n);
+int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, cudaStream_t stream);
 }  // namespace ofdm
 
 #define OFDM_FOR_EACH_N(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
