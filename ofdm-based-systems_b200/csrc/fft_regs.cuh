@@ -114,4 +114,61 @@ __device__ __forceinline__ void fft_dif_inplace(float2 (&v)[R]) {
 template <int R>
 __host__ __device__ constexpr int fft_out_index(int k) { return cx_brev(k, cx_log2(R)); }
 
+// Decimation-in-time butterfly with the compile-time twiddle W = W_NN^I applied to c, FMA-fused:
+//   (a, c) <- (a + W c, a - W c).   General twiddles cost 6 instructions (4 FFMA for a + W c, then
+//   a - W c = 2 a - (a + W c) as 2 FFMA); trivial ones 4 FADD; the 45-degree ones 2 FADD + 4 FFMA.
+template <int I, int NN, int DIR>
+__device__ __forceinline__ void dit_butterfly(float2& a, float2& c) {
+  static_assert(I >= 0 && 2 * I < NN, "twiddle index");
+  if constexpr (I == 0) {
+    const float2 lo = cadd(a, c), hi = csub(a, c);
+    a = lo;
+    c = hi;
+  } else if constexpr (4 * I == NN) {  // W = -j (forward) / +j (inverse)
+    const float2 wc = DIR < 0 ? make_float2(c.y, -c.x) : make_float2(-c.y, c.x);
+    const float2 lo = cadd(a, wc), hi = csub(a, wc);
+    a = lo;
+    c = hi;
+  } else if constexpr (8 * I == NN || 8 * I == 3 * NN) {
+    constexpr float h = 0.70710678118654752440f;
+    float t1, t2;  // W c = h * (t1, t2)
+    if constexpr (8 * I == NN) {
+      t1 = DIR < 0 ? c.x + c.y : c.x - c.y;
+      t2 = DIR < 0 ? c.y - c.x : c.x + c.y;
+    } else {
+      t1 = DIR < 0 ? c.y - c.x : -(c.x + c.y);
+      t2 = DIR < 0 ? -(c.x + c.y) : c.x - c.y;
+    }
+    const float2 lo = make_float2(fmaf(h, t1, a.x), fmaf(h, t2, a.y));
+    const float2 hi = make_float2(fmaf(-h, t1, a.x), fmaf(-h, t2, a.y));
+    a = lo;
+    c = hi;
+  } else {
+    constexpr float wr = (float)cx_cos_frac(I, NN);
+    constexpr float wi = (float)(DIR < 0 ? -cx_sin_frac(I, NN) : cx_sin_frac(I, NN));
+    const float2 lo = make_float2(fmaf(-wi, c.y, fmaf(wr, c.x, a.x)), fmaf(wi, c.x, fmaf(wr, c.y, a.y)));
+    const float2 hi = make_float2(fmaf(2.0f, a.x, -lo.x), fmaf(2.0f, a.y, -lo.y));
+    a = lo;
+    c = hi;
+  }
+}
+
+// In-place decimation-in-time FFT of R points in registers.  Same convention as fft_dif_inplace: input
+// element n in v[n], output element k in v[fft_out_index<R>(k)] (working slot j lives in v[brev j]).
+template <int R, int DIR>
+__device__ __forceinline__ void fft_dit_inplace(float2 (&v)[R]) {
+  static_assert((R & (R - 1)) == 0 && R >= 1, "radix must be a power of two");
+  constexpr int LOG = cx_log2(R);
+  static_for<LOG>([&](auto S) {
+    constexpr int half = 1 << decltype(S)::value;
+    constexpr int span = 2 * half;
+    static_for<R / span>([&](auto B) {
+      static_for<half>([&](auto I) {
+        constexpr int lo = decltype(B)::value * span + decltype(I)::value, hi = lo + half;
+        dit_butterfly<decltype(I)::value, span, DIR>(v[cx_brev(lo, LOG)], v[cx_brev(hi, LOG)]);
+      });
+    });
+  });
+}
+
 }  // namespace ofdm

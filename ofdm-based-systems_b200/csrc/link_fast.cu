@@ -2,14 +2,15 @@
 #include "link_fast.cuh"
 #include "plan.h"
 
+#include <cstdlib>
+
 namespace ofdm {
 
-template <int E, bool DUMP>
+template <int E, bool DUMP, int BLOCK = 512, int SYNC = 2>
 static int launch_fast_e(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
-  using G = FastGeometry<E>;
-  auto kern = ofdm_link_fast_kernel<E, DUMP, true>;
-  static int occ_cache[2] = {0, 0};
-  int& occ = occ_cache[DUMP ? 1 : 0];
+  using G = FastGeometry<E, BLOCK>;
+  auto kern = ofdm_link_fast_kernel<E, DUMP, true, BLOCK, SYNC>;
+  static int occ = 0;
   if (occ == 0) {
     if (G::SMEM_BYTES > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
@@ -32,7 +33,17 @@ int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, cudaStream_t
   switch (L->d.n_subcarriers) {
     case 64: return dump ? launch_fast_e<8, true>(L, p, stream) : launch_fast_e<8, false>(L, p, stream);
     case 256: return dump ? launch_fast_e<16, true>(L, p, stream) : launch_fast_e<16, false>(L, p, stream);
-    case 1024: return dump ? launch_fast_e<32, true>(L, p, stream) : launch_fast_e<32, false>(L, p, stream);
+    case 1024: {
+      if (dump) return launch_fast_e<32, true>(L, p, stream);
+      static const int variant = [] { const char* v = std::getenv("OFDM_B200_FAST_VARIANT"); return v ? std::atoi(v) : 0; }();
+      switch (variant) {
+        case 1: return launch_fast_e<32, false, 512, 1>(L, p, stream);
+        case 3: return launch_fast_e<32, false, 512, 3>(L, p, stream);
+        case 4: return launch_fast_e<32, false, 512, 0>(L, p, stream);
+        case 5: return launch_fast_e<32, false, 256, 2>(L, p, stream);
+        default: return launch_fast_e<32, false>(L, p, stream);
+      }
+    }
     default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", L->d.n_subcarriers);
   }
 }

@@ -1,14 +1,17 @@
 // ofdm_link_fast kernel: the Monte-Carlo hot loop for the common link shape
 //   OFDM modulator, square QAM of one order on every subcarrier (4 .. 256), cyclic prefix at least as long
-//   as the channel memory (no inter-symbol interference), <= 8 taps, Philox bits and noise,
-//   N = E*E subcarriers with E in {8, 16, 32}  (N = 64, 256, 1024).
+//   as the channel memory (no inter-symbol interference) and at most E samples, <= 8 taps, Philox bits and
+//   noise, N = E*E subcarriers with E in {8, 16, 32}  (N = 64, 256, 1024).
 // Same chain and same reference lines as link_kernel.cuh; what differs is the machine mapping:
-//   * a team of E lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers,
-//   * the instruction working set is kept inside the instruction cache: ONE forward-FFT body serves both
-//     transforms (the IFFT runs as FFT on re/im-swapped data), the FIR + AWGN stage is a rolled loop over
-//     8-sample chunks that works in place in shared memory,
-//   * all scale factors (1/sqrt(2(M-1)/3), the two 1/sqrt(N), the slicer's k/2) are folded on the host into
-//     the FIR taps and the equaliser table, level <-> index conversions use mantissa tricks (no I2F/F2I),
+//   * a team of E lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers;
+//   * ONE forward-FFT body serves both transforms (the IFFT runs as an FFT on re/im-swapped data) and the
+//     FIR + AWGN stage is a rolled loop over 8-sample chunks that works in place in shared memory, so the
+//     per-symbol instruction stream stays small; the warps that share a scheduler walk it in step (named
+//     barrier per scheduler) so that they share instruction-cache lines;
+//   * every scale factor (1/sqrt(2(M-1)/3), both 1/sqrt(N), the slicer's k/2 and 1/(s-1)) is folded on the
+//     host into the FIR taps and the equaliser table; level <-> index conversions use mantissa tricks and
+//     FFMA.SAT (no I2F / F2I / FMNMX);
+//   * ZF and "no equaliser" run through the MMSE form conj(A) / (G + sigma2) with sigma2 = 0;
 //   * bit errors are counted on packed words: gray^-1 is linear over GF(2), so the error pattern of a
 //     subcarrier is gray^-1(col_tx ^ col_rx), evaluated four subcarriers per 32-bit word.
 #pragma once
@@ -24,16 +27,14 @@ namespace ofdm {
 constexpr int kFastTaps = 8;
 
 struct FastParams {
-  float2 taps[kFastTaps];   // unit-energy taps * 1 / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1))
-  const float4* eq_tab;     // MMSE {Re H", Im H", |H|^2, -} with H" = H k / (2 sqrt N); ZF {Re g, Im g, -, -}
+  float2 taps[kFastTaps];   // unit-energy taps / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1), IFFT unscaled)
+  const float4* eq_tab;     // {Re A, Im A, G, -}: decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1)
   const float2* tw;         // pass-2 twiddles exp(-2 pi i t r / N) at [(r-1)*E + t]
   float sigma;              // per-component noise standard deviation
-  float mmse_c;             // sigma2_eq = mmse_c * sum_k |Y~_k|^2   (Y~ = unscaled FFT output)
-  float slice_off;          // (s-1)/2
+  float mmse_c;             // MMSE: sigma2 = mmse_c * sum_k |Y~_k|^2 (Y~ = unscaled FFT output); else unused
   float slice_top;          // s-1
   float tx_scale2;          // |tx|^2 = tx_scale2 * |x~|^2 (PAPR statistics)
-  float z_unscale;          // DUMP only: Z = (t - slice_off) * z_unscale  (= 2 / k)
-  float noeq_scale;         // equaliser NONE: t = Re(Y~) * noeq_scale + slice_off  (= k / (2 sqrt N))
+  float z_unscale;          // DUMP only: Z = (Y~ conj A / (G + sigma2)) * z_unscale   (= 2 (s-1) / k)
   int prefix_len;
   int equalizer;
   int half_bits;            // log2(s)
@@ -50,16 +51,28 @@ struct FastParams {
   float2* dump_noise;
 };
 
-template <int E>
+template <int E, int BLOCK_ = 512>
 struct FastGeometry {
   static constexpr int N = E * E;
   static constexpr int T = E;                 // lanes per OFDM symbol
   static constexpr int RS = E + 2;            // row stride (complex): conflict-free 128-bit row accesses
   static constexpr int TEAM_F2 = E * RS;      // float2 per team
-  static constexpr int BLOCK = 128;
+  static constexpr int BLOCK = BLOCK_;
   static constexpr int TEAMS = BLOCK / T;
-  static constexpr size_t SMEM_BYTES = size_t(TEAMS) * TEAM_F2 * sizeof(float2);
+  static constexpr int TW_F2 = (E - 1) * E;   // twiddle table (float2)
+  static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4);
 };
+
+// SYNC = 0: warps run free.  SYNC = 1: __syncthreads() at the section boundaries.  SYNC >= 2: named barrier
+// among the warps that share a scheduler (warp id mod 4); SYNC = 3 also inside the FIR loop.
+template <int SYNC, int BLOCK>
+__device__ __forceinline__ void section_sync() {
+  if constexpr (SYNC == 1) {
+    __syncthreads();
+  } else if constexpr (SYNC >= 2) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + ((threadIdx.x >> 5) & 3)), "n"(BLOCK / 4) : "memory");
+  }
+}
 
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;
@@ -77,32 +90,40 @@ __device__ __forceinline__ float fast_lg2(float x) {
   return y;
 }
 
-// circularly-symmetric N(0,1)+jN(0,1) from two 32-bit words (same distribution as box_muller())
+// circularly-symmetric sigma * (N(0,1) + j N(0,1)) from two 32-bit words (same distribution as box_muller())
 __device__ __forceinline__ float2 fast_box_muller(uint32_t wr, uint32_t wa, float sigma) {
   const float u1 = fmaf((float)wr, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float rad = sigma * fast_sqrt(-1.3862943611198906f * fast_lg2(u1));  // sqrt(-2 ln u)
+  const float rad = sigma * fast_sqrt(-1.3862943611198906f * fast_lg2(u1));  // sigma * sqrt(-2 ln u)
   const float ang = (float)(int32_t)wa * 1.4629180792671596e-09f;            // (-pi, pi)
   return make_float2(rad * __cosf(ang), rad * __sinf(ang));
 }
 
-// prefix-XOR inside the 4-bit fields that sit at bits 1..4 / 5..8 of every byte (inverse Gray code)
+// prefix-XOR inside the 4-bit fields that sit at bits 1..4 of every byte (inverse Gray code)
 __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   x ^= x >> 1;
   x ^= x >> 2;
   return x;
 }
 
-template <int E, bool DUMP, bool PAPR>
-__global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(const FastParams p) {
-  using G = FastGeometry<E>;
+template <int E, bool DUMP, bool PAPR, int BLOCK = 512, int SYNC = 2>
+__global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+  using G = FastGeometry<E, BLOCK>;
   constexpr int N = G::N, T = G::T, RS = G::RS, WORDS = E / 4;
   constexpr int CALLS = (E + 15) / 16;  // Philox calls for E random bytes
   extern __shared__ float4 smem4[];
   const int lane = threadIdx.x & 31;
   const int t = lane % T;
   const int team_in_block = threadIdx.x / T;
-  float2* buf = reinterpret_cast<float2*>(smem4) + size_t(team_in_block) * G::TEAM_F2;
+  float2* smem2 = reinterpret_cast<float2*>(smem4);
+  float2* buf = smem2 + size_t(team_in_block) * G::TEAM_F2;
   float2* row = buf + t * RS;
+  float2* s_tw = smem2 + size_t(G::TEAMS) * G::TEAM_F2;
+  float4* s_eq = reinterpret_cast<float4*>(s_tw + G::TW_F2);
+
+  // block-resident copies of the twiddle and equaliser tables
+  for (int i = threadIdx.x; i < G::TW_F2; i += BLOCK) s_tw[i] = __ldg(&p.tw[i]);
+  for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[i]);
+  __syncthreads();
 
   const unsigned long long n_teams = (unsigned long long)gridDim.x * G::TEAMS;
   const unsigned long long team_id = (unsigned long long)blockIdx.x * G::TEAMS + team_in_block;
@@ -121,11 +142,12 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
     const unsigned long long gs = p.sym_begin + (active ? s : 0ull);
     const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
 
-    unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1.. of each byte
+    unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1..4 of each byte
     float2 v[E];
 
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
+      section_sync<SYNC, BLOCK>();
       if (phase == 0) {
         // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
         //      low nibble -> column (in-phase) index, high nibble -> row (quadrature) index.
@@ -168,6 +190,7 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
         __syncwarp();
 #pragma unroll 1
         for (int c = 0; c < E / 8; ++c) {
+          if constexpr (SYNC >= 3) section_sync<SYNC, BLOCK>();
           float2 cur[8], y[8];
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
@@ -195,7 +218,7 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
               const uint32_t pair = uint32_t((E * t + 8 * c) >> 1) + j;
               const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (1u << 28) | pair, p.point), key);
               const float2 g0 = fast_box_muller(w.x, w.y, p.sigma), g1 = fast_box_muller(w.z, w.w, p.sigma);
-              if (DUMP) {
+              if constexpr (DUMP) {
                 if (active && p.dump_noise) {
                   float2* dn = p.dump_noise + s * (unsigned long long)(N + P) + P + E * t + 8 * c + 2 * j;
                   dn[0] = g0;
@@ -216,10 +239,11 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[m * RS + t];
         __syncwarp();
+        section_sync<SYNC, BLOCK>();
       }
 
       // ---- forward FFT of N = E*E points: radix-E in registers, row/column exchange, twiddle, radix-E
-      fft_dif_inplace<E, -1>(v);
+      fft_dit_inplace<E, -1>(v);
 #pragma unroll
       for (int r = 0; r < E; r += 2) {
         const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
@@ -230,9 +254,10 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
 #pragma unroll
       for (int m = 0; m < E; ++m) u[m] = buf[m * RS + t];
       __syncwarp();
+      section_sync<SYNC, BLOCK>();
 #pragma unroll
-      for (int r = 1; r < E; ++r) u[r] = cmul(u[r], __ldg(&p.tw[(r - 1) * T + t]));
-      fft_dif_inplace<E, -1>(u);
+      for (int r = 1; r < E; ++r) u[r] = cmul(u[r], s_tw[(r - 1) * T + t]);
+      fft_dit_inplace<E, -1>(u);
 
       if (phase == 0) {
         // ---- x~[t + T m] = swap(u[brev m]); PAPR statistics; publish for the FIR (prefix/models.py:34-44)
@@ -241,10 +266,10 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
         for (int m = 0; m < E; ++m) {
           const float2 o = u[fft_out_index<E>(m)];
           const float2 x = make_float2(o.y, o.x);
-          if (PAPR) {
+          if constexpr (PAPR) {
             const float pw = fmaf(x.x, x.x, x.y * x.y);
-            const int n = t + T * m;
-            ssum += (n >= N - P) ? 2.f * pw : pw;   // the cyclic prefix repeats the last P samples
+            // the cyclic prefix repeats the last P <= E samples: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
+            ssum += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
             smax = fmaxf(smax, pw);
           }
           buf[m * RS + t] = x;
@@ -273,30 +298,16 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
         for (int m = 0; m < E; ++m) {
           const float2 yv = u[fft_out_index<E>(m)];
           const int k = t + T * m;
-          float tc, tr;
-          if (p.equalizer == EQ_NONE) {
-            tc = fmaf(yv.x, p.noeq_scale, p.slice_off);
-            tr = fmaf(-yv.y, p.noeq_scale, p.slice_off);
-          } else {
-            const float4 e = __ldg(&p.eq_tab[k]);
-            float a, b, inv = 1.f;
-            if (p.equalizer == EQ_MMSE) {
-              a = fmaf(yv.x, e.x, yv.y * e.y);          // Re(Y conj H")
-              b = fmaf(yv.x, e.y, -yv.y * e.x);         // -Im(Y conj H")
-              inv = fast_rcp(e.z + sigma2);
-            } else {
-              a = fmaf(yv.x, e.x, -yv.y * e.y);         // Re(Y g)
-              b = -fmaf(yv.x, e.y, yv.y * e.x);         // -Im(Y g)
-            }
-            tc = fmaf(a, inv, p.slice_off);
-            tr = fmaf(b, inv, p.slice_off);
+          const float4 e = s_eq[k];
+          const float a = fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
+          const float b = fmaf(yv.x, e.y, -yv.y * e.x);   // -Im(Y conj A)
+          const float inv = fast_rcp(e.z + sigma2);
+          if constexpr (DUMP) {
+            if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * p.z_unscale, -b * inv * p.z_unscale);
           }
-          if (DUMP) {
-            if (active && p.dump_z)
-              p.dump_z[s * N + k] = make_float2((tc - p.slice_off) * p.z_unscale, (p.slice_off - tr) * p.z_unscale);
-          }
-          tc = fminf(fmaxf(tc, 0.f), p.slice_top) + magic;   // low mantissa bits = rint(clamped)
-          tr = fminf(fmaxf(tr, 0.f), p.slice_top) + magic;
+          // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
+          const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), p.slice_top, magic);
+          const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), p.slice_top, magic);
           // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
           rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
           rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(FastGeometry<E>::BLOCK) ofdm_link_fast_kernel(
           any |= any >> 2;
           any |= any >> 1;
           se += __popc(any & 0x02020202u);
-          if (DUMP) {
+          if constexpr (DUMP) {
             if (active) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {

@@ -279,7 +279,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
     L->fast = uniform && !amp && (M == 4 || M == 16 || M == 64 || M == 256) && desc->scheme == OFDM_SCHEME_QAM &&
               desc->modulator == OFDM_MOD_OFDM && desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 &&
-              Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1');
+              Lt <= kFastTaps && fast_supports_n(N) && P * P <= N && !(force && force[0] == '1');
     if (L->fast) {
       L->fixed_order = M;
       const double knorm = std::sqrt(2.0 * (M - 1) / 3.0), sqn = std::sqrt((double)N);
@@ -288,14 +288,18 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
       for (int l = 0; l < kFastTaps; ++l)
         L->taps_fast[l] = l < Lt ? make_float2((float)(taps_chan[2 * l] * tap_scale), (float)(taps_chan[2 * l + 1] * tap_scale))
                                  : make_float2(0.f, 0.f);
-      const double dec = knorm / (2.0 * sqn);               // slicer scale k/2 and the receiver's 1/sqrt(N)
+      // decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1):  k/2 (slicer), 1/sqrt(N) (receiver FFT)
+      // and 1/(s-1) (unit interval for FFMA.SAT) folded into A
+      int side = 1;
+      while (side * side < M) side *= 2;
+      const double dec = knorm / (2.0 * sqn * (side - 1));
       std::vector<float4> eqf(N);
       for (int k = 0; k < N; ++k) {
         const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
-        if (desc->equalizer == OFDM_EQ_ZF) {
-          const std::complex<double> h = (H == std::complex<double>(0.0, 0.0)) ? std::complex<double>(1e-10, 0.0) : H;
-          const std::complex<double> g = dec / h;
-          eqf[k] = make_float4((float)g.real(), (float)g.imag(), 0.f, 0.f);
+        if (desc->equalizer == OFDM_EQ_NONE) {
+          eqf[k] = make_float4((float)dec, 0.f, 1.f, 0.f);
+        } else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) {
+          eqf[k] = make_float4((float)(dec * 1e10), 0.f, 1.f, 0.f);   // equalization/models.py:33-35: h := 1e-10
         } else {
           eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), 0.f);
         }
@@ -372,12 +376,10 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     f.sigma = (float)noise_sigma;
     const double snr_lin = std::pow(10.0, snr_db / 10.0);
     f.mmse_c = L->mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
-    f.slice_off = 0.5f * float(side - 1);
     f.slice_top = float(side - 1);
     const double tap_scale = 1.0 / (L->knorm * std::sqrt((double)N));
     f.tx_scale2 = (float)(tap_scale * tap_scale);
-    f.z_unscale = (float)(2.0 / L->knorm);
-    f.noeq_scale = (float)(L->knorm / (2.0 * std::sqrt((double)N)));
+    f.z_unscale = (float)(2.0 * (side - 1) / L->knorm);
     f.prefix_len = L->d.prefix_len;
     f.equalizer = L->d.equalizer;
     f.half_bits = half_bits;
