@@ -6,10 +6,10 @@
 
 namespace ofdm {
 
-template <int E, bool DUMP, int BLOCK = 512, int SYNC = 2>
+template <int E, bool DUMP, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10, int FIR_UNROLL = 2>
 static int launch_fast_e(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
   using G = FastGeometry<E, BLOCK>;
-  auto kern = ofdm_link_fast_kernel<E, DUMP, true, BLOCK, SYNC>;
+  auto kern = ofdm_link_fast_kernel<E, DUMP, true, BLOCK, SYNC, NROUNDS, FIR_UNROLL>;
   static int occ = 0;
   if (occ == 0) {
     if (G::SMEM_BYTES > 48 * 1024)
@@ -41,6 +41,10 @@ int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, cudaStream_t
         case 3: return launch_fast_e<32, false, 512, 3>(L, p, stream);
         case 4: return launch_fast_e<32, false, 512, 0>(L, p, stream);
         case 5: return launch_fast_e<32, false, 256, 2>(L, p, stream);
+        case 6: return launch_fast_e<32, false, 512, 2, 7, 2>(L, p, stream);
+        case 7: return launch_fast_e<32, false, 512, 2, 10, 1>(L, p, stream);
+        case 8: return launch_fast_e<32, false, 640, 0>(L, p, stream);
+        case 9: return launch_fast_e<32, false, 512, 0, 10, 4>(L, p, stream);
         default: return launch_fast_e<32, false>(L, p, stream);
       }
     }

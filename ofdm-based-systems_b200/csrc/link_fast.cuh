@@ -98,6 +98,17 @@ __device__ __forceinline__ float2 fast_box_muller(uint32_t wr, uint32_t wa, floa
   return make_float2(rad * __cosf(ang), rad * __sinf(ang));
 }
 
+// sigma * (N(0,1) + j N(0,1)) from a 32-bit radius word and a 16-bit angle field (bytes picked by `sel`):
+//   radius = sqrt(-2 sigma^2 ln u), u = (w + 0.5) 2^-32  -> tail out to 6.6 sigma;
+//   angle  = 2 pi a / 65536 - pi via the mantissa of 2^23 + a (noise is rotation invariant, 16 bits suffice)
+__device__ __forceinline__ float2 fast_noise(uint32_t wr, uint32_t wa, uint32_t sel, float c2 /* -2 sigma^2 ln 2 */) {
+  const float u1 = fmaf((float)wr, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float rad = fast_sqrt(c2 * fast_lg2(u1));
+  const float f = __uint_as_float(__byte_perm(wa, 0x4B000000u, sel));           // 2^23 + a
+  const float ang = fmaf(f, 9.587379924285257e-05f, -807.3893119735271f);       // (2 pi / 65536) a - pi
+  return make_float2(rad * __cosf(ang), rad * __sinf(ang));
+}
+
 // prefix-XOR inside the 4-bit fields that sit at bits 1..4 of every byte (inverse Gray code)
 __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   x ^= x >> 1;
@@ -105,7 +116,7 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   return x;
 }
 
-template <int E, bool DUMP, bool PAPR, int BLOCK = 512, int SYNC = 2>
+template <int E, bool DUMP, bool PAPR, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10, int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
   using G = FastGeometry<E, BLOCK>;
   constexpr int N = G::N, T = G::T, RS = G::RS, WORDS = E / 4;
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   const PhiloxKey key{(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
   const int P = p.prefix_len;
   const float magic = 8388608.0f;  // 2^23
+  const float noise_c2 = -1.3862943611198906f * p.sigma * p.sigma;
 
   unsigned long long acc_bit_err = 0, acc_sym_err = 0, acc_syms = 0;
   double acc_pow = 0.0;
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           }
         }
         __syncwarp();
-#pragma unroll 1
+#pragma unroll FIR_UNROLL
         for (int c = 0; c < E / 8; ++c) {
           if constexpr (SYNC >= 3) section_sync<SYNC, BLOCK>();
           float2 cur[8], y[8];
@@ -213,20 +225,20 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             y[i] = make_float2(yr, yi);
           }
           if (p.sigma > 0.f) {
+            // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
+            const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
+            const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, p.point), key);
+            const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), p.point), key);
+            const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), p.point), key);
+            const uint32_t rw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const uint32_t aw[4] = {wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t pair = uint32_t((E * t + 8 * c) >> 1) + j;
-              const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (1u << 28) | pair, p.point), key);
-              const float2 g0 = fast_box_muller(w.x, w.y, p.sigma), g1 = fast_box_muller(w.z, w.w, p.sigma);
+            for (int i = 0; i < 8; ++i) {
+              const float2 g = fast_noise(rw[i], aw[i >> 1], (i & 1) ? 0x7632u : 0x7610u, noise_c2);
               if constexpr (DUMP) {
-                if (active && p.dump_noise) {
-                  float2* dn = p.dump_noise + s * (unsigned long long)(N + P) + P + E * t + 8 * c + 2 * j;
-                  dn[0] = g0;
-                  dn[1] = g1;
-                }
+                if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + P + E * t + 8 * c + i] = g;
               }
-              y[2 * j] = cadd(y[2 * j], g0);
-              y[2 * j + 1] = cadd(y[2 * j + 1], g1);
+              y[i] = cadd(y[i], g);
             }
           }
 #pragma unroll
