@@ -272,6 +272,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   L->mean_h2 = sum_h2 / N;
 
   // ---- fast-path eligibility (link_fast.cuh) and its folded tables
+  std::vector<float4> eq_fast_host;
   {
     bool uniform = true;
     for (int k = 1; k < N; ++k) uniform = uniform && (orders[k] == orders[0]);
@@ -304,27 +305,33 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
           eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), 0.f);
         }
       }
-      CUDA_TRY(cudaMalloc(&L->d_eq_fast, N * sizeof(float4)));
-      CUDA_TRY(cudaMemcpy(L->d_eq_fast, eqf.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
+      eq_fast_host.swap(eqf);
     }
   }
 
   int rc = configure(L);
   if (rc != OFDM_OK) { delete L; return rc; }
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-  L->sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaDeviceGetAttribute(&L->sms, cudaDevAttrMultiProcessorCount, dev));
 
+  // one device arena, one host->device copy: [counters | sc | eq | eq_fast | twiddles]
   const std::vector<float2> tw = build_twiddles(N, L->E);
-  CUDA_TRY(cudaMalloc(&L->d_sc, N * sizeof(float4)));
-  CUDA_TRY(cudaMalloc(&L->d_eq, N * sizeof(float4)));
-  CUDA_TRY(cudaMalloc(&L->d_tw, tw.size() * sizeof(float2)));
-  CUDA_TRY(cudaMalloc(&L->d_cnt, sizeof(CounterBlock)));
-  CUDA_TRY(cudaMemcpy(L->d_sc, sc.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(L->d_eq, eq.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(L->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemset(L->d_cnt, 0, sizeof(CounterBlock)));
-  L->table_bytes = 2 * size_t(N) * sizeof(float4) + tw.size() * sizeof(float2);
+  const size_t off_sc = 256, off_eq = off_sc + N * sizeof(float4), off_eqf = off_eq + N * sizeof(float4),
+               off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), total = off_tw + tw.size() * sizeof(float2);
+  std::vector<unsigned char> stage(total, 0);
+  std::memcpy(stage.data() + off_sc, sc.data(), N * sizeof(float4));
+  std::memcpy(stage.data() + off_eq, eq.data(), N * sizeof(float4));
+  if (!eq_fast_host.empty()) std::memcpy(stage.data() + off_eqf, eq_fast_host.data(), eq_fast_host.size() * sizeof(float4));
+  std::memcpy(stage.data() + off_tw, tw.data(), tw.size() * sizeof(float2));
+  unsigned char* arena = nullptr;
+  CUDA_TRY(cudaMalloc(&arena, total));
+  L->arena = arena;
+  CUDA_TRY(cudaMemcpy(arena, stage.data(), total, cudaMemcpyHostToDevice));
+  L->d_cnt = reinterpret_cast<CounterBlock*>(arena);
+  L->d_sc = reinterpret_cast<float4*>(arena + off_sc);
+  L->d_eq = reinterpret_cast<float4*>(arena + off_eq);
+  L->d_eq_fast = eq_fast_host.empty() ? nullptr : reinterpret_cast<float4*>(arena + off_eqf);
+  L->d_tw = reinterpret_cast<float2*>(arena + off_tw);
+  L->table_bytes = total;
   *out = L;
   return OFDM_OK;
 }
@@ -332,11 +339,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
 void ofdm_link_destroy(ofdm_link* L) {
   if (!L) return;
   DeviceGuard guard(L->device);
-  cudaFree(L->d_sc);
-  cudaFree(L->d_eq);
-  cudaFree(L->d_tw);
-  cudaFree(L->d_cnt);
-  cudaFree(L->d_eq_fast);
+  cudaFree(L->arena);
   delete L;
 }
 

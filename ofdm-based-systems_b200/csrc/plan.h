@@ -42,6 +42,7 @@ struct ofdm_link {
   float4* d_eq = nullptr;
   float2* d_tw = nullptr;
   ofdm::CounterBlock* d_cnt = nullptr;
+  unsigned char* arena = nullptr;  // single device allocation behind all the pointers above
   int device = 0, sms = 0, occ = 1;
   size_t smem = 0;
   size_t table_bytes = 0;

@@ -83,6 +83,39 @@ class _DeviceWords:
 N_WORDS = 10  # 8 x uint64 counters, double power sum, uint64 bits of the double power max
 
 
+def combine_counters(rows, rank: int, world: int, group=None):
+    """rows: int64 tensor [points, 10] holding each point's raw counter block of THIS rank (8 uint64
+    counters, the bit pattern of the double power sum, the bit pattern of the double power max).
+    Packs them so that ONE SUM all-reduce combines everything: counters and power sums add (counts
+    below 2^53 are exact in float64), and every rank writes its maximum into its own slot so that the
+    element-wise sum carries all the maxima.  Works on any device / backend (NCCL on GPUs, gloo in the
+    CPU tests).  Returns the float64 tensor [points, 9 + world]."""
+    import torch
+    import torch.distributed as dist
+    payload = torch.zeros((rows.shape[0], 9 + world), dtype=torch.float64, device=rows.device)
+    payload[:, :8] = rows[:, :8].to(torch.float64)
+    payload[:, 8] = rows[:, 8].contiguous().view(torch.float64)
+    payload[:, 9 + rank] = rows[:, 9].contiguous().view(torch.float64)
+    if world > 1:
+        dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+    return payload
+
+
+def decode_counters(snr_dbs: Sequence[float], payload, samples_per_ofdm_symbol: int) -> List[dict]:
+    host = payload.cpu().numpy()
+    out = []
+    for i, snr in enumerate(snr_dbs):
+        c = host[i]
+        bit_errors, bits, sym_errors, syms, ofdm = (int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]))
+        mean_p = c[8] / max(ofdm * samples_per_ofdm_symbol, 1)
+        out.append(dict(snr_db=float(snr), bit_errors=bit_errors, total_bits=bits, symbol_errors=sym_errors,
+                        num_constellation_symbols=syms, num_ofdm_symbols=ofdm,
+                        bit_error_rate=bit_errors / bits if bits else 0.0,
+                        symbol_error_rate=sym_errors / syms if syms else 0.0,
+                        papr_db=float(10 * np.log10(c[9:].max() / mean_p)) if mean_p > 0 else float("inf")))
+    return out
+
+
 class LinkSweep:
     def __init__(self, cfg: LinkConfig, device: Optional[int] = None):
         self.cfg = cfg
@@ -132,31 +165,12 @@ class LinkSweep:
             self.link.launch_fused(float(snr), self.cfg.noise_sigma(float(snr)), count, seed=seed, point=i,
                                    first_symbol=first, stream=stream)
             rows[i].copy_(block)
-        # one SUM all-reduce carries the counters, the power sums and (one slot per rank) the maxima
-        payload = torch.zeros((k, 9 + world), dtype=torch.float64, device=dev)
-        payload[:, :8] = rows[:, :8].to(torch.float64)           # counts < 2^53 are exact in float64
-        payload[:, 8] = rows[:, 8].view(torch.float64)
-        payload[:, 9 + rank] = rows[:, 9].view(torch.float64)
-        if distributed and world > 1:
-            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
-        return payload
+        return combine_counters(rows, rank, world, group if distributed else None)
 
     def finalize(self, snr_dbs: Sequence[float], payload) -> List[dict]:
         """Device -> host read of the combined counters; result keys follow the reference's result dict
         (bit_errors / total_bits / bit_error_rate / symbol_errors / symbol_error_rate / papr_db)."""
-        host = payload.cpu().numpy()
-        n_pre = self.cfg.num_subcarriers + self.cfg.prefix_length
-        out = []
-        for i, snr in enumerate(snr_dbs):
-            c = host[i]
-            bit_errors, bits, sym_errors, syms, ofdm = (int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]))
-            mean_p = c[8] / max(ofdm * n_pre, 1)
-            out.append(dict(snr_db=float(snr), bit_errors=bit_errors, total_bits=bits, symbol_errors=sym_errors,
-                            num_constellation_symbols=syms, num_ofdm_symbols=ofdm,
-                            bit_error_rate=bit_errors / bits if bits else 0.0,
-                            symbol_error_rate=sym_errors / syms if syms else 0.0,
-                            papr_db=float(10 * np.log10(c[9:].max() / mean_p)) if mean_p > 0 else float("inf")))
-        return out
+        return decode_counters(snr_dbs, payload, self.cfg.num_subcarriers + self.cfg.prefix_length)
 
     def sweep(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
               weak_scaling: bool = False) -> List[dict]:
