@@ -119,6 +119,33 @@ void* ofdm_link_counters_device_ptr(ofdm_link* link);
 /* kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t ofdm_b200_launch_count(void);
 
+/* Batched water-filling + gap-rule bit loading, one channel realisation per row (fp64 on the device).
+ * Replaces, per realisation: gains = |fft(raw taps, N)|^2 (simulation/models.py:277-278),
+ * WaterfillingPowerAllocation.allocate / _find_water_level (power_allocation/models.py:140-225) or
+ * UniformPowerAllocation.allocate (:61-69), the reported water level (simulation/models.py:311-313) and
+ * calculate_bit_loading_order per subcarrier (constellation/models.py:297-321 QAM, :459-474 PSK). */
+typedef struct ofdm_waterfill_desc {
+  int32_t n_subcarriers;
+  int32_t n_taps;
+  int32_t scheme;        /* OFDM_SCHEME_* selects the gap rule                                            */
+  int32_t waterfilling;  /* 1 = water-filling, 0 = uniform allocation                                     */
+  int32_t min_order;     /* honoured only when max_order > 0 (the reference never clamps)     */
+  int32_t max_order;
+  double snr_db;         /* N0 = 10^(-snr_db/10)                                                          */
+  double total_power;    /* N in adaptive mode, 1.0 in fixed mode (simulation/models.py:297, 486)         */
+  double gap;            /* QAM: Qinv(ser/4)^2 / 3;  PSK: Qinv(ser/2)^2 / (2 pi^2)   (caller: scipy norm.isf) */
+  double tolerance;      /* bisection stop, default 1e-8                                                  */
+} ofdm_waterfill_desc;
+/* taps: [n][n_taps] complex128 RAW taps; outputs power [n][N] f64, orders [n][N] i32, water_level [n] f64 (NaN
+ * when uniform), optional h_eq [n][N] complex128 and iterations [n] i32.  HOST buffers, synchronous. */
+int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* desc, const double* taps, int64_t n_realisations,
+                                   double* power, int32_t* orders, double* water_level, double* h_eq,
+                                   int32_t* iterations);
+/* same on DEVICE buffers, asynchronous on `stream` */
+int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* desc, const double* taps_dev, int64_t n_realisations,
+                                       double* power_dev, int32_t* orders_dev, double* water_level_dev,
+                                       double* h_eq_dev, int32_t* iterations_dev, void* stream);
+
 /* FP32 FFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per FFMA) on the current device,
  * the roofline denominator SURVEY 8(d) asks for; <0 on error. */
 double ofdm_b200_measure_fp32_tflops(int32_t iters);

@@ -39,6 +39,12 @@ class LinkResult(C.Structure):
                 ("tx_power_sum", C.c_double), ("tx_power_max", C.c_double)]
 
 
+class WaterfillDesc(C.Structure):
+    _fields_ = [("n_subcarriers", C.c_int32), ("n_taps", C.c_int32), ("scheme", C.c_int32), ("waterfilling", C.c_int32),
+                ("min_order", C.c_int32), ("max_order", C.c_int32), ("snr_db", C.c_double), ("total_power", C.c_double),
+                ("gap", C.c_double), ("tolerance", C.c_double)]
+
+
 class LinkDump(C.Structure):
     _fields_ = [("y", C.c_void_p), ("z", C.c_void_p), ("rx_labels", C.c_void_p), ("tx_labels", C.c_void_p),
                 ("noise", C.c_void_p)]
@@ -49,6 +55,7 @@ EXPORTS = (
     "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
     "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr",
+    "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev",
 )
 
 
@@ -79,6 +86,8 @@ def _load() -> C.CDLL:
     lib.ofdm_link_read_result.argtypes = [vp, vp, C.POINTER(LinkResult)]
     lib.ofdm_link_counters_device_ptr.argtypes = [vp]
     lib.ofdm_link_counters_device_ptr.restype = vp
+    lib.ofdm_waterfill_bitload_batched.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp]
+    lib.ofdm_waterfill_bitload_batched_dev.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     if lib.ofdm_b200_abi_version() != 1:
         raise NativeLibraryMissing(f"{LIB_PATH}: ABI version {lib.ofdm_b200_abi_version()} != 1, rebuild it")
     return lib
@@ -238,6 +247,37 @@ class Link:
     @property
     def counters_device_ptr(self) -> int:
         return int(lib.ofdm_link_counters_device_ptr(self._h) or 0)
+
+
+def bit_loading_gap(ser: float, scheme: str = "QAM") -> float:
+    """The SNR gap of the reference's bit-loading rules: QAM Qinv(ser/4)^2/3 (constellation/models.py:301-304),
+    PSK gamma* = Qinv(ser/2)^2 / (2 pi^2) (:462-464).  scipy's norm.isf, like the reference."""
+    from scipy.stats import norm
+    if scheme == "QAM":
+        return float(norm.isf(ser / 4) ** 2 / 3)
+    return float(norm.isf(ser / 2) ** 2 / (2 * np.pi ** 2))
+
+
+def waterfill_bitload_batched(taps: np.ndarray, n_subcarriers: int, snr_db: float, *, ser: float = 1e-3,
+                              total_power: Optional[float] = None, scheme: str = "QAM", waterfilling: bool = True,
+                              min_order: int = 0, max_order: int = 0, tolerance: float = 1e-8):
+    """Power allocation + gap-rule orders for a batch of channel realisations on the GPU.
+    taps: [F, L] complex RAW taps.  Returns dict(power [F,N], orders [F,N], water_level [F], h_eq [F,N],
+    iterations [F])."""
+    require_gpu()
+    taps = np.ascontiguousarray(np.atleast_2d(taps), dtype=np.complex128)
+    f, l = taps.shape
+    n = int(n_subcarriers)
+    desc = WaterfillDesc(n, l, SCHEME[scheme], int(bool(waterfilling)), int(min_order), int(max_order), float(snr_db),
+                         float(n if total_power is None else total_power), bit_loading_gap(ser, scheme), float(tolerance))
+    power = np.empty((f, n), dtype=np.float64)
+    orders = np.empty((f, n), dtype=np.int32)
+    level = np.empty(f, dtype=np.float64)
+    h_eq = np.empty((f, n), dtype=np.complex128)
+    iters = np.empty(f, dtype=np.int32)
+    _check(lib.ofdm_waterfill_bitload_batched(C.byref(desc), taps.ctypes.data, f, power.ctypes.data, orders.ctypes.data,
+                                              level.ctypes.data, h_eq.ctypes.data, iters.ctypes.data))
+    return dict(power=power, orders=orders.astype(np.int64), water_level=level, h_eq=h_eq, iterations=iters)
 
 
 def measure_fp32_tflops(iters: int = 4096) -> float:

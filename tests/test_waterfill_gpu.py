@@ -1,0 +1,54 @@
+"""Batched water-filling + bit-loading kernel against the oracle / the reference's fixtures."""
+import numpy as np
+import pytest
+
+import ofdm_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shipped_channels_match_reference(kat):
+    from ofdm_based_systems._native import waterfill_bitload_batched
+    names = [str(n) for n in kat["channel_names"]]
+    for n_sc in (64, 1024):
+        for snr in (5.0, 20.0):
+            for nm in names:                       # tap counts differ -> one call per channel
+                out = waterfill_bitload_batched(kat["chan_" + nm][None, :], n_sc, snr)
+                key = f"wf_{nm}_{n_sc}_{int(snr)}"
+                np.testing.assert_allclose(out["power"][0], kat[key + "_power"], rtol=1e-7, atol=1e-9)
+                np.testing.assert_array_equal(out["orders"][0], kat[key + "_orders"])
+                np.testing.assert_allclose(out["h_eq"][0], np.fft.fft(kat["chan_" + nm], n_sc), rtol=0, atol=1e-13)
+
+
+def test_random_rayleigh_batch_matches_oracle():
+    """config #4 shape: a fresh 8-tap Rayleigh realisation per frame (examples/generate_channel_models.py:70-78)."""
+    from ofdm_based_systems._native import waterfill_bitload_batched
+    rng = np.random.default_rng(42)
+    f, l, n = 200, 8, 256
+    taps = (rng.normal(size=(f, l)) + 1j * rng.normal(size=(f, l))) * np.sqrt(np.exp(-np.arange(l) / 2))
+    taps /= np.sqrt(np.sum(np.abs(taps) ** 2, axis=1, keepdims=True))
+    for scheme, wf in (("QAM", True), ("PSK", True), ("QAM", False)):
+        out = waterfill_bitload_batched(taps, n, 18.0, scheme=scheme, waterfilling=wf)
+        mism = 0
+        for i in range(f):
+            orders, power, level = oc.adaptive_setup(n, taps[i], 18.0, 1e-3, scheme, waterfill=wf)
+            np.testing.assert_allclose(out["power"][i], power, rtol=1e-7, atol=1e-9)
+            mism += int(np.sum(out["orders"][i] != orders))
+            if wf:
+                assert abs(out["water_level"][i] - level) < 1e-6 * abs(level)
+            else:
+                assert np.isnan(out["water_level"][i])
+        assert mism <= 2          # a subcarrier may sit within 1e-9 of a rounding edge of log2(1 + snr/gap)
+    bounded = waterfill_bitload_batched(taps, n, 30.0, min_order=4, max_order=256)
+    assert bounded["orders"].max() <= 256 and set(np.unique(bounded["orders"])) <= {0, 4, 16, 64, 256}
+
+
+def test_known_answers():
+    from ofdm_based_systems._native import waterfill_bitload_batched
+    # the water-filling KATs are stated on gains, not taps: a 1-tap channel with |h|^2 = g per "subcarrier" is not
+    # expressible, so check the iteration count and level on a flat channel instead (all floors equal)
+    out = waterfill_bitload_batched(np.array([[1.0 + 0j]]), 64, 10.0, total_power=64.0)
+    np.testing.assert_allclose(out["power"][0], np.ones(64), rtol=1e-12)
+    assert out["iterations"][0] <= 100
+    with pytest.raises(ValueError):
+        waterfill_bitload_batched(np.array([[1.0 + 0j]]), 64, 10.0, total_power=-1.0)
