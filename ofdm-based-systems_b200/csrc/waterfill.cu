@@ -194,8 +194,10 @@ int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* d, const double* t
   const size_t F = (size_t)n_realisations, N = (size_t)d->n_subcarriers, L = (size_t)d->n_taps;
   if (F == 0) return OFDM_OK;
   unsigned char* arena = nullptr;
-  const size_t o_taps = 0, o_pow = o_taps + F * L * 16, o_ord = o_pow + F * N * 8, o_lvl = o_ord + ((F * N * 4 + 7) & ~size_t(7)),
-               o_heq = o_lvl + F * 8, o_it = o_heq + (h_eq ? F * N * 16 : 0), total = o_it + F * 4;
+  auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };   // double2 accesses need 16-byte alignment
+  const size_t o_taps = 0, o_pow = up16(o_taps + F * L * 16), o_ord = up16(o_pow + F * N * 8),
+               o_lvl = up16(o_ord + F * N * 4), o_heq = up16(o_lvl + F * 8), o_it = up16(o_heq + (h_eq ? F * N * 16 : 0)),
+               total = o_it + F * 4;
   CUDA_TRY(cudaMalloc(&arena, total));
   int rc = OFDM_OK;
   cudaError_t e = cudaMemcpy(arena + o_taps, taps, F * L * 16, cudaMemcpyHostToDevice);
