@@ -163,7 +163,8 @@ def run_b200_arm(args) -> None:
     _native.require_gpu()
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=90))
     dev = torch.device("cuda", local)
 
     cfg = LinkConfig(num_subcarriers=N_SC, taps_raw=headline_taps(), constellation_order=ORDER,
@@ -182,14 +183,14 @@ def run_b200_arm(args) -> None:
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        # ---- warm-up: at least W steps and at least ~0.6 s under load, so that nvidia-smi (100 ms period)
-        #      sees the clocks this kernel actually runs at before and during the timed region
-        t_warm, w = time.perf_counter(), 0
-        while w < max(args.warmup, 3) or time.perf_counter() - t_warm < 0.6:
+        # ---- warm-up: W steps (>= 3), then a FIXED number of extra steps (~0.6 s under load; the count must be
+        #      identical on every rank because each step ends in a collective) so that nvidia-smi (100 ms
+        #      period) samples the clocks this kernel actually runs at
+        w = max(args.warmup, 3) + 500
+        for i in range(w):
             flush.zero_()
-            sweep.enqueue(snrs, S, seed=w, weak_scaling=True)
-            w += 1
-            if w % 16 == 0:
+            sweep.enqueue(snrs, S, seed=i, weak_scaling=True)
+            if i % 16 == 15:
                 torch.cuda.synchronize()
         barrier()
         # ---- timed region: EXACTLY K steps, device-timed, counters stay on the device
