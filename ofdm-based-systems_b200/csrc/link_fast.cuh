@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             }
             y[i] = make_float2(yr, yi);
           }
-          if (p.sigma > 0.f) {
+          {  // unconditional (sigma = 0 scales the samples to zero): keeping FIR and noise in ONE basic block
+             // lets ptxas interleave the Philox / MUFU chains with the FIR's FFMAs
             // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
             const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
             const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, p.point), key);
@@ -256,6 +257,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 
       // ---- forward FFT of N = E*E points: radix-E in registers, row/column exchange, twiddle, radix-E
       fft_dit_inplace<E, -1>(v);
+#ifdef OFDM_SYNC_BEFORE_STORE
+      section_sync<SYNC, BLOCK>();
+#endif
 #pragma unroll
       for (int r = 0; r < E; r += 2) {
         const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
@@ -266,14 +270,16 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
       for (int m = 0; m < E; ++m) u[m] = buf[m * RS + t];
       __syncwarp();
+#ifndef OFDM_SYNC_BEFORE_STORE
       section_sync<SYNC, BLOCK>();
+#endif
 #pragma unroll
       for (int r = 1; r < E; ++r) u[r] = cmul(u[r], s_tw[(r - 1) * T + t]);
       fft_dit_inplace<E, -1>(u);
 
       if (phase == 0) {
         // ---- x~[t + T m] = swap(u[brev m]); PAPR statistics; publish for the FIR (prefix/models.py:34-44)
-        float ssum = 0.f, smax = 0.f;
+        float ssum[4] = {0.f, 0.f, 0.f, 0.f}, smax[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains: latency, not issue
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           const float2 o = u[fft_out_index<E>(m)];
@@ -281,28 +287,28 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           if constexpr (PAPR) {
             const float pw = fmaf(x.x, x.x, x.y * x.y);
             // the cyclic prefix repeats the last P <= E samples: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
-            ssum += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
-            smax = fmaxf(smax, pw);
+            ssum[m & 3] += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
+            smax[m & 3] = fmaxf(smax[m & 3], pw);
           }
           buf[m * RS + t] = x;
         }
         if (PAPR && active) {
-          acc_pow += double(ssum);
-          acc_max = fmaxf(acc_max, smax);
+          acc_pow += double((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));
+          acc_max = fmaxf(acc_max, fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3])));
         }
         __syncwarp();
       } else {
         // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
         //      simulation/models.py:597-606)
-        float sigma2 = 0.f;
-        if (p.equalizer == EQ_MMSE) {
-          float ss = 0.f;
+        // per-symbol MMSE noise estimate; branch-free (mmse_c = 0 for ZF / none) so that the shuffle latency
+        // overlaps the per-subcarrier products below
+        float sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int m = 0; m < E; ++m) ss = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, ss));
+        for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
+        float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
 #pragma unroll
-          for (int off = T / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-          sigma2 = ss * p.mmse_c;
-        }
+        for (int off = T / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        const float sigma2 = ss * p.mmse_c;
         unsigned rxc[WORDS], rxr[WORDS];
 #pragma unroll
         for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;

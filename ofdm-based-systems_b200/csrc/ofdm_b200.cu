@@ -378,7 +378,7 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     f.tw = L->d_tw;
     f.sigma = (float)noise_sigma;
     const double snr_lin = std::pow(10.0, snr_db / 10.0);
-    f.mmse_c = L->mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
+    f.mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f : L->mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
     f.slice_top = float(side - 1);
     const double tap_scale = 1.0 / (L->knorm * std::sqrt((double)N));
     f.tx_scale2 = (float)(tap_scale * tap_scale);
