@@ -78,6 +78,9 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
                      const int32_t* orders, const double* amp, ofdm_link** out);
 void ofdm_link_destroy(ofdm_link* link);
 int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* link);
+/* 1 when this link shape runs on the register-resident fast kernel (csrc/link_fast.cuh), 0 when it runs on
+ * the general kernel (csrc/link_kernel.cuh); both compute the same chain */
+int ofdm_link_uses_fast_kernel(const ofdm_link* link);
 /* bytes ofdm_link_create copied host -> device for this link (tables; bench.py's h2d accounting) */
 uint64_t ofdm_link_table_bytes(const ofdm_link* link);
 

@@ -51,6 +51,9 @@ def _units():
         units.append(("waterfill", os.path.join(CSRC, "waterfill.cu"), []))
     if os.path.exists(os.path.join(CSRC, "link_fast.cu")):
         units.append(("link_fast", os.path.join(CSRC, "link_fast.cu"), []))
+    if os.path.exists(os.path.join(CSRC, "link_fast_inst.cu")):
+        for e in (8, 16, 32):
+            units.append((f"link_fast_inst_{e}", os.path.join(CSRC, "link_fast_inst.cu"), [f"-DOFDM_FAST_E={e}"]))
     for n in SIZES:
         units.append((f"link_inst_{n}", os.path.join(CSRC, "link_inst.cu"), [f"-DOFDM_INST_N={n}"]))
     return units

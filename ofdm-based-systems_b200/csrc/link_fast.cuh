@@ -49,6 +49,14 @@ struct FastParams {
   unsigned short* dump_rx;
   unsigned short* dump_tx;
   float2* dump_noise;
+  float2* dump_y;           // DUMP only: ortho-scaled FFT output before the equaliser
+  float y_scale;            // 1 / sqrt(N)
+  // REPLAY instantiation: the reference's own byte stream (MSB first) and complex64 noise over the serial
+  // stream, (N + P) samples per OFDM symbol (bits_generation/models.py:27-55, noise/models.py:19-22)
+  const unsigned char* bits;
+  unsigned long long bits_len;
+  const void* noise;        // complex64 (noise_f64 = 0) or complex128 (noise_f64 = 1); NULL = noiseless
+  int noise_f64;
 };
 
 template <int E, int BLOCK_ = 512>
@@ -116,7 +124,8 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   return x;
 }
 
-template <int E, bool DUMP, bool PAPR, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10, int FIR_UNROLL = 2>
+template <int E, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10,
+          int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
   using G = FastGeometry<E, BLOCK>;
   constexpr int N = G::N, T = G::T, RS = G::RS, WORDS = E / 4;
@@ -163,15 +172,50 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
       if (phase == 0) {
         // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
         //      low nibble -> column (in-phase) index, high nibble -> row (quadrature) index.
+        if constexpr (REPLAY) {
+          // the symbol's N*bps/8 bytes -> shared memory as big-endian words (coalesced loads); label k = t + T m is
+          // the bps bits at bit offset k*bps, MSB first (constellation/models.py:226-243): a funnel shift over two
+          // words.  column = gray(label & (s-1)), row = gray(label >> log2 s); gray is applied on packed words.
+          const int bps = 2 * p.half_bits, sym_words = N * bps / 32;
+          unsigned* wscr = reinterpret_cast<unsigned*>(buf);
+          const unsigned long long base = (active ? s : 0ull) * (unsigned long long)(4 * sym_words);
+          for (int w = t; w <= sym_words; w += T)
+            wscr[w] = w < sym_words ? __byte_perm(__ldg(reinterpret_cast<const unsigned*>(p.bits + base) + w), 0u, 0x0123) : 0u;
+          // pull the symbol's recorded noise towards L2 while the transmitter runs
+          if (p.noise) {
+            const int nbytes = (p.noise_f64 ? 16 : 8) * (N + P);
+            const char* nz = reinterpret_cast<const char*>(p.noise) + (active ? s : 0ull) * (unsigned long long)nbytes;
+            for (int l = t * 128; l < nbytes; l += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nz + l));
+          }
+          __syncwarp();
 #pragma unroll
-        for (int c = 0; c < CALLS; ++c) {
-          const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), p.point), key);
-          const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+          for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
+          const unsigned smask = (1u << p.half_bits) - 1u;
+          const int bit0 = t * bps, tb = T * bps;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (4 * c + j < WORDS) {
-              txc[4 * c + j] = (ww[j] << 1) & p.field_mask;   // bits 0..3 of each byte -> column index
-              txr[4 * c + j] = (ww[j] >> 3) & p.field_mask;   // bits 4..7 of each byte -> row index
+          for (int m = 0; m < E; ++m) {
+            const int bit = bit0 + m * tb, w = bit >> 5;
+            const unsigned lab = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31) >> (32 - bps);
+            txc[m >> 2] |= (lab & smask) << (8 * (m & 3) + 1);
+            txr[m >> 2] |= (lab >> p.half_bits) << (8 * (m & 3) + 1);
+          }
+#pragma unroll
+          for (int j = 0; j < WORDS; ++j) {
+            txc[j] = (txc[j] ^ (txc[j] >> 1)) & p.field_mask;
+            txr[j] = (txr[j] ^ (txr[j] >> 1)) & p.field_mask;
+          }
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int c = 0; c < CALLS; ++c) {
+            const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), p.point), key);
+            const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (4 * c + j < WORDS) {
+                txc[4 * c + j] = (ww[j] << 1) & p.field_mask;   // bits 0..3 of each byte -> column index
+                txr[4 * c + j] = (ww[j] >> 3) & p.field_mask;   // bits 4..7 of each byte -> row index
+              }
             }
           }
         }
@@ -226,20 +270,22 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           }
           {  // unconditional (sigma = 0 scales the samples to zero): keeping FIR and noise in ONE basic block
              // lets ptxas interleave the Philox / MUFU chains with the FIR's FFMAs
-            // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
-            const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
-            const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, p.point), key);
-            const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), p.point), key);
-            const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), p.point), key);
-            const uint32_t rw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-            const uint32_t aw[4] = {wc.x, wc.y, wc.z, wc.w};
+            if constexpr (!REPLAY) {
+              // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
+              const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
+              const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, p.point), key);
+              const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), p.point), key);
+              const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), p.point), key);
+              const uint32_t rw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+              const uint32_t aw[4] = {wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 g = fast_noise(rw[i], aw[i >> 1], (i & 1) ? 0x7632u : 0x7610u, noise_c2);
-              if constexpr (DUMP) {
-                if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + P + E * t + 8 * c + i] = g;
+              for (int i = 0; i < 8; ++i) {
+                const float2 g = fast_noise(rw[i], aw[i >> 1], (i & 1) ? 0x7632u : 0x7610u, noise_c2);
+                if constexpr (DUMP) {
+                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + P + E * t + 8 * c + i] = g;
+                }
+                y[i] = cadd(y[i], g);
               }
-              y[i] = cadd(y[i], g);
             }
           }
 #pragma unroll
@@ -251,6 +297,22 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[m * RS + t];
+        if constexpr (REPLAY) {
+          // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples
+          const unsigned long long ni = (active ? s : 0ull) * (unsigned long long)(N + P) + P + t;
+          if (p.noise && !p.noise_f64) {
+            const float2* nz = reinterpret_cast<const float2*>(p.noise) + ni;
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cadd(v[m], __ldg(nz + T * m));
+          } else if (p.noise) {
+            const double2* nz = reinterpret_cast<const double2*>(p.noise) + ni;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+              const double2 g = __ldg(nz + T * m);
+              v[m] = cadd(v[m], make_float2((float)g.x, (float)g.y));
+            }
+          }
+        }
         __syncwarp();
         section_sync<SYNC, BLOCK>();
       }
@@ -321,6 +383,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const float b = fmaf(yv.x, e.y, -yv.y * e.x);   // -Im(Y conj A)
           const float inv = fast_rcp(e.z + sigma2);
           if constexpr (DUMP) {
+            if (active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
             if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * p.z_unscale, -b * inv * p.z_unscale);
           }
           // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index

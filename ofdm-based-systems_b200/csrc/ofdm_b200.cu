@@ -110,6 +110,42 @@ void set_dump(LinkParams& p, const ofdm_link_dump* d) {
   p.dump_noise = reinterpret_cast<float2*>(d->noise);
 }
 
+// parameter block of the fast kernel (link_fast.cuh) for one SNR point
+void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link_dump* dump_dev) {
+  const int N = L->d.n_subcarriers, M = L->fixed_order;
+  int half_bits = 0;
+  while ((1 << (2 * half_bits)) < M) ++half_bits;
+  const int side = 1 << half_bits;
+  std::memset(&f, 0, sizeof(f));
+  std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
+  f.eq_tab = L->d_eq_fast;
+  f.tw = L->d_tw;
+  const double snr_lin = std::pow(10.0, snr_db / 10.0);
+  // equalization/models.py:43-49 on the unscaled FFT output Y~ = sqrt(N) Y
+  f.mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f
+             : L->mean_h2 == 0.0            ? INFINITY
+                                            : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
+  f.slice_top = float(side - 1);
+  const double tap_scale = 1.0 / (L->knorm * std::sqrt((double)N));
+  f.tx_scale2 = (float)(tap_scale * tap_scale);
+  f.z_unscale = (float)(2.0 * (side - 1) / L->knorm);
+  f.y_scale = (float)(1.0 / std::sqrt((double)N));
+  f.prefix_len = L->d.prefix_len;
+  f.equalizer = L->d.equalizer;
+  f.half_bits = half_bits;
+  f.field_mask = 0x01010101u * (unsigned)((side - 1) << 1);
+  f.counters = L->d_cnt->cnt;
+  f.tx_power_sum = &L->d_cnt->power_sum;
+  f.tx_power_max_bits = &L->d_cnt->power_max_bits;
+  if (dump_dev) {
+    f.dump_y = reinterpret_cast<float2*>(dump_dev->y);
+    f.dump_z = reinterpret_cast<float2*>(dump_dev->z);
+    f.dump_rx = dump_dev->rx_labels;
+    f.dump_tx = dump_dev->tx_labels;
+    f.dump_noise = reinterpret_cast<float2*>(dump_dev->noise);
+  }
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -344,6 +380,7 @@ void ofdm_link_destroy(ofdm_link* L) {
 }
 
 int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* L) { return L ? L->bits_per_ofdm : OFDM_EINVAL; }
+int ofdm_link_uses_fast_kernel(const ofdm_link* L) { return L ? L->fast : OFDM_EINVAL; }
 uint64_t ofdm_link_table_bytes(const ofdm_link* L) { return L ? L->table_bytes : 0; }
 void* ofdm_link_counters_device_ptr(ofdm_link* L) { return L ? (void*)L->d_cnt : nullptr; }
 
@@ -365,42 +402,16 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
   if (!L) return fail(OFDM_EINVAL, "null link");
   if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
   DeviceGuard guard(L->device);
-  if (L->fast && !(dump_dev && dump_dev->y)) {
+  if (L->fast) {
     // common link shape: the fast kernel (link_fast.cuh); its Philox streams are its own
-    const int N = L->d.n_subcarriers, M = L->fixed_order;
-    int half_bits = 0;
-    while ((1 << (2 * half_bits)) < M) ++half_bits;
-    const int side = 1 << half_bits;
     FastParams f;
-    std::memset(&f, 0, sizeof(f));
-    std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
-    f.eq_tab = L->d_eq_fast;
-    f.tw = L->d_tw;
+    fill_fast(L, f, snr_db, dump_dev);
     f.sigma = (float)noise_sigma;
-    const double snr_lin = std::pow(10.0, snr_db / 10.0);
-    f.mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f : L->mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
-    f.slice_top = float(side - 1);
-    const double tap_scale = 1.0 / (L->knorm * std::sqrt((double)N));
-    f.tx_scale2 = (float)(tap_scale * tap_scale);
-    f.z_unscale = (float)(2.0 * (side - 1) / L->knorm);
-    f.prefix_len = L->d.prefix_len;
-    f.equalizer = L->d.equalizer;
-    f.half_bits = half_bits;
-    f.field_mask = 0x01010101u * (unsigned)((side - 1) << 1);
     f.seed = seed;
     f.point = point;
     f.sym_begin = first_symbol;
     f.sym_count = n_symbols;
-    f.counters = L->d_cnt->cnt;
-    f.tx_power_sum = &L->d_cnt->power_sum;
-    f.tx_power_max_bits = &L->d_cnt->power_max_bits;
-    if (dump_dev) {
-      f.dump_z = reinterpret_cast<float2*>(dump_dev->z);
-      f.dump_rx = dump_dev->rx_labels;
-      f.dump_tx = dump_dev->tx_labels;
-      f.dump_noise = reinterpret_cast<float2*>(dump_dev->noise);
-    }
-    return launch_fast(L, f, dump_dev != nullptr, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, false, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);
@@ -424,6 +435,19 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
   if (noise_dtype != OFDM_NOISE_NONE && !noise_dev) return fail(OFDM_EINVAL, "noise buffer missing");
   if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
   DeviceGuard guard(L->device);
+  const uint64_t whole = n_symbols * (uint64_t)L->bits_per_ofdm;
+  if (L->fast && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
+      (reinterpret_cast<uintptr_t>(bits_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(noise_dev) & 15) == 0) {
+    // common link shape, whole OFDM symbols: the fast kernel streams the recorded bits and noise
+    FastParams f;
+    fill_fast(L, f, snr_db, dump_dev);
+    f.bits = bits_dev;
+    f.bits_len = n_bytes;
+    f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
+    f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
+    f.sym_count = n_symbols;
+    return launch_fast(L, f, dump_dev != nullptr, true, (cudaStream_t)stream);
+  }
   LinkParams p;
   fill_params(L, p, snr_db);
   p.bits_src = SRC_REPLAY_F32;

@@ -63,7 +63,7 @@ template <int N> int launch_kernel(const ofdm_link* L, const LinkParams& p, cuda
 namespace ofdm {
 struct FastParams;
 bool fast_supports_n(int n);
-int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, cudaStream_t stream);
+int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
 }  // namespace ofdm
 
 #define OFDM_FOR_EACH_N(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)

@@ -53,6 +53,7 @@ class LinkDump(C.Structure):
 EXPORTS = (
     "ofdm_b200_last_error", "ofdm_b200_abi_version", "ofdm_b200_device_count", "ofdm_b200_launch_count",
     "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
+    "ofdm_link_uses_fast_kernel",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
     "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr",
     "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev",
@@ -77,6 +78,7 @@ def _load() -> C.CDLL:
     lib.ofdm_link_destroy.restype = None
     lib.ofdm_link_bits_per_ofdm_symbol.argtypes = [vp]
     lib.ofdm_link_table_bytes.argtypes = [vp]
+    lib.ofdm_link_uses_fast_kernel.argtypes = [vp]
     lib.ofdm_link_table_bytes.restype = u64
     lib.ofdm_link_run_fused.argtypes = [vp, dbl, dbl, u64, u32, u64, u64, C.POINTER(LinkDump), C.POINTER(LinkResult)]
     lib.ofdm_link_run_replay.argtypes = [vp, dbl, vp, u64, vp, i32, u64, u64, C.POINTER(LinkDump), C.POINTER(LinkResult)]
@@ -167,6 +169,7 @@ class Link:
                                     None if a is None else a.ctypes.data, C.byref(self._h)))
         self.bits_per_ofdm_symbol = int(lib.ofdm_link_bits_per_ofdm_symbol(self._h))
         self.table_bytes = int(lib.ofdm_link_table_bytes(self._h))
+        self.uses_fast_kernel = bool(lib.ofdm_link_uses_fast_kernel(self._h))
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -40,14 +40,27 @@ def rel_err(a, ref):
     return float(np.max(np.abs(a - ref)) / np.max(np.abs(ref)))
 
 
+# golden cases whose link shape the register-resident fast kernel covers (csrc/link_fast.cuh)
+FAST_CASES = {"headline_n1024_64qam_mmse", "c2_n1024_16qam_mmse", "c3_n64_64qam_mmse_p2", "c3_n64_64qam_zf_p2"}
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
 @pytest.mark.parametrize("noise_dtype", [np.complex128, np.complex64])
 @pytest.mark.parametrize("name", golden_link_names())
-def test_replay_matches_reference(name, noise_dtype):
+def test_replay_matches_reference(name, noise_dtype, kernel, monkeypatch):
     g = load_golden("link", name)
+    if kernel == "general":
+        monkeypatch.setenv("OFDM_B200_FORCE_GENERAL", "1")     # read by ofdm_link_create
     n, n_ofdm = int(g["n_sc"]), int(g["n_ofdm"])
     setup, ref = oracle_run(g)
     assert ref["bit_errors"] == int(g["bit_errors"])          # the oracle itself is pinned to the reference
     link = make_link(g)
+    if kernel == "general":
+        assert not link.uses_fast_kernel
+    elif name in FAST_CASES:
+        assert link.uses_fast_kernel, "this link shape must run on the fast kernel"
+    elif not link.uses_fast_kernel:
+        pytest.skip("general kernel only: covered by kernel=general")
     noise = g["noise"].astype(noise_dtype) if bool(g["awgn"]) else None
     res, d = link.run_replay(float(g["snr_db"]), g["tx_bytes"].tobytes(), noise, n_ofdm,
                              compare_limit_bits=8 * g["tx_bytes"].size, dump=("y", "z", "rx_labels", "tx_labels"))
