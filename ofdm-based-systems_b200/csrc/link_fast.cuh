@@ -157,6 +157,24 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   double acc_pow = 0.0;
   float acc_max = 0.f;
 
+  unsigned next_bits[REPLAY ? WORDS : 1];
+  auto replay_prefetch = [&](unsigned long long sn) {
+    if constexpr (REPLAY) {
+      if (sn >= p.sym_count) return;
+      const int sym_words = N * 2 * p.half_bits / 32;
+      const unsigned* src = reinterpret_cast<const unsigned*>(p.bits) + sn * (unsigned long long)sym_words;
+#pragma unroll
+      for (int j = 0; j < WORDS; ++j)
+        if (t + T * j < sym_words) next_bits[j] = __ldg(src + t + T * j);
+      if (p.noise) {
+        const int nbytes = (p.noise_f64 ? 16 : 8) * (N + P);
+        const char* nz = reinterpret_cast<const char*>(p.noise) + sn * (unsigned long long)nbytes;
+        for (int l = t * 128; l < nbytes; l += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nz + l));
+      }
+    }
+  };
+  replay_prefetch(team_id);
+
   for (unsigned long long it = 0; it < iters; ++it) {
     const unsigned long long s = it * n_teams + team_id;
     const bool active = s < p.sym_count;
@@ -178,15 +196,12 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           // words.  column = gray(label & (s-1)), row = gray(label >> log2 s); gray is applied on packed words.
           const int bps = 2 * p.half_bits, sym_words = N * bps / 32;
           unsigned* wscr = reinterpret_cast<unsigned*>(buf);
-          const unsigned long long base = (active ? s : 0ull) * (unsigned long long)(4 * sym_words);
-          for (int w = t; w <= sym_words; w += T)
-            wscr[w] = w < sym_words ? __byte_perm(__ldg(reinterpret_cast<const unsigned*>(p.bits + base) + w), 0u, 0x0123) : 0u;
-          // pull the symbol's recorded noise towards L2 while the transmitter runs
-          if (p.noise) {
-            const int nbytes = (p.noise_f64 ? 16 : 8) * (N + P);
-            const char* nz = reinterpret_cast<const char*>(p.noise) + (active ? s : 0ull) * (unsigned long long)nbytes;
-            for (int l = t * 128; l < nbytes; l += T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nz + l));
-          }
+#pragma unroll
+          for (int j = 0; j < WORDS; ++j)
+            if (t + T * j < sym_words) wscr[t + T * j] = __byte_perm(next_bits[j], 0u, 0x0123);
+          if (t == 0) wscr[sym_words] = 0u;
+          // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
+          replay_prefetch(s + n_teams);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
@@ -298,7 +313,8 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[m * RS + t];
         if constexpr (REPLAY) {
-          // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples
+          // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples (the lines
+          // were pulled into L2 one OFDM symbol ago)
           const unsigned long long ni = (active ? s : 0ull) * (unsigned long long)(N + P) + P + t;
           if (p.noise && !p.noise_f64) {
             const float2* nz = reinterpret_cast<const float2*>(p.noise) + ni;

@@ -41,10 +41,9 @@ int launch_fast_width<OFDM_FAST_E>(const ofdm_link* L, const FastParams& p, bool
     if (dump) return launch_fast_kernel<E, true, true>(L, p, stream);
 #if OFDM_FAST_E == 32
     static const int rvariant = [] { const char* v = std::getenv("OFDM_B200_REPLAY_VARIANT"); return v ? std::atoi(v) : 0; }();
-    if (rvariant == 1) return launch_fast_kernel<E, false, true, 512, 2>(L, p, stream);
+    if (rvariant == 1) return launch_fast_kernel<E, false, true, 512, 0>(L, p, stream);
 #endif
-    // free-running warps: the recorded-noise loads of one warp overlap the arithmetic of the others
-    return launch_fast_kernel<E, false, true, 512, 0>(L, p, stream);
+    return launch_fast_kernel<E, false, true>(L, p, stream);
   }
   if (dump) return launch_fast_kernel<E, true, false>(L, p, stream);
 #if OFDM_FAST_E == 32
