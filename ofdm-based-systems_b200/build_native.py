@@ -52,8 +52,9 @@ def _units():
     if os.path.exists(os.path.join(CSRC, "link_fast.cu")):
         units.append(("link_fast", os.path.join(CSRC, "link_fast.cu"), []))
     if os.path.exists(os.path.join(CSRC, "link_fast_inst.cu")):
-        for e in (8, 16, 32):
-            units.append((f"link_fast_inst_{e}", os.path.join(CSRC, "link_fast_inst.cu"), [f"-DOFDM_FAST_E={e}"]))
+        for e, t in ((8, 8), (16, 16), (32, 32), (32, 64), (32, 128)):
+            units.append((f"link_fast_inst_{e}x{t}", os.path.join(CSRC, "link_fast_inst.cu"),
+                          [f"-DOFDM_FAST_E={e}", f"-DOFDM_FAST_T={t}"]))
     for n in SIZES:
         units.append((f"link_inst_{n}", os.path.join(CSRC, "link_inst.cu"), [f"-DOFDM_INST_N={n}"]))
     return units

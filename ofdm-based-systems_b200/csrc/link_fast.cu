@@ -1,20 +1,23 @@
 // Dispatch of the fast-path kernel (link_fast.cuh); the kernels are instantiated in link_fast_inst.cu,
-// one translation unit per team width E (nvcc -DOFDM_FAST_E=<E>) so that the build parallelises.
+// one translation unit per team shape (nvcc -DOFDM_FAST_E=<E> -DOFDM_FAST_T=<T>) so that the build parallelises.
 #include "link_fast.cuh"
 #include "plan.h"
 
 namespace ofdm {
 
-template <int E>
-int launch_fast_width(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
+template <int E, int T>
+int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
 
-bool fast_supports_n(int n) { return n == 64 || n == 256 || n == 1024; }
+bool fast_supports_n(int n) { return n == 64 || n == 256 || n == 1024 || n == 2048 || n == 4096; }
+int fast_samples_per_lane(int n) { return n == 64 ? 8 : n == 256 ? 16 : 32; }
 
 int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream) {
   switch (L->d.n_subcarriers) {
-    case 64: return launch_fast_width<8>(L, p, dump, replay, stream);
-    case 256: return launch_fast_width<16>(L, p, dump, replay, stream);
-    case 1024: return launch_fast_width<32>(L, p, dump, replay, stream);
+    case 64: return launch_fast_shape<8, 8>(L, p, dump, replay, stream);
+    case 256: return launch_fast_shape<16, 16>(L, p, dump, replay, stream);
+    case 1024: return launch_fast_shape<32, 32>(L, p, dump, replay, stream);
+    case 2048: return launch_fast_shape<32, 64>(L, p, dump, replay, stream);
+    case 4096: return launch_fast_shape<32, 128>(L, p, dump, replay, stream);
     default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", L->d.n_subcarriers);
   }
 }

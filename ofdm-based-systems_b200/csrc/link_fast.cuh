@@ -1,7 +1,9 @@
 // ofdm_link_fast kernel: the Monte-Carlo hot loop for the common link shape
 //   OFDM modulator, square QAM of one order on every subcarrier (4 .. 256), cyclic prefix at least as long
 //   as the channel memory (no inter-symbol interference) and at most E samples, <= 8 taps, Philox bits and
-//   noise, N = E*E subcarriers with E in {8, 16, 32}  (N = 64, 256, 1024).
+//   noise, N = E*T subcarriers: a team of T lanes with E samples per lane.  T = E in {8, 16, 32}
+//   (N = 64, 256, 1024: two-pass transform, the team fits one warp); T = 2E or 4E with E = 32 (N = 2048, 4096:
+//   the team spans 2 or 4 warps, a third radix-2/4 pass follows a second exchange).
 // Same chain and same reference lines as link_kernel.cuh; what differs is the machine mapping:
 //   * a team of E lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers;
 //   * ONE forward-FFT body serves both transforms (the IFFT runs as an FFT on re/im-swapped data) and the
@@ -29,7 +31,8 @@ constexpr int kFastTaps = 8;
 struct FastParams {
   float2 taps[kFastTaps];   // unit-energy taps / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1), IFFT unscaled)
   const float4* eq_tab;     // {Re A, Im A, G, -}: decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1)
-  const float2* tw;         // pass-2 twiddles exp(-2 pi i t r / N) at [(r-1)*E + t]
+  const float2* tw;         // pass-2 twiddles exp(-2 pi i k r / E^2) at [(r-1)*E + k], then (T > E) the pass-3 base
+                            // twiddles exp(-2 pi i j / N), j < N / (T/E)
   float sigma;              // per-component noise standard deviation
   float mmse_c;             // MMSE: sigma2 = mmse_c * sum_k |Y~_k|^2 (Y~ = unscaled FFT output); else unused
   float slice_top;          // s-1
@@ -59,17 +62,33 @@ struct FastParams {
   int noise_f64;
 };
 
-template <int E, int BLOCK_ = 512>
+template <int E, int T_ = E, int BLOCK_ = 512>
 struct FastGeometry {
-  static constexpr int N = E * E;
-  static constexpr int T = E;                 // lanes per OFDM symbol
+  static_assert(T_ % E == 0 && (T_ == E || E == 32), "team = whole warps when it is wider than E");
+  static constexpr int T = T_;                // lanes per OFDM symbol
+  static constexpr int N = E * T;
+  static constexpr int W = T / E;             // radix of the third pass (1: two-pass transform)
   static constexpr int RS = E + 2;            // row stride (complex): conflict-free 128-bit row accesses
-  static constexpr int TEAM_F2 = E * RS;      // float2 per team
+  static constexpr int TEAM_F2 = T * RS;      // float2 per team: T rows of E samples
   static constexpr int BLOCK = BLOCK_;
   static constexpr int TEAMS = BLOCK / T;
-  static constexpr int TW_F2 = (E - 1) * E;   // twiddle table (float2)
-  static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4);
+  static constexpr int TW2_F2 = (E - 1) * E;  // pass-2 twiddles (float2)
+  static constexpr int TW3_F2 = W > 1 ? N / W : 0;
+  static constexpr int TW_F2 = TW2_F2 + TW3_F2;
+  static constexpr int RED_F = W > 1 ? TEAMS * W : 0;   // cross-warp reduction scratch (floats)
+  static constexpr size_t SMEM_BYTES =
+      (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) + RED_F * sizeof(float);
 };
+
+// barrier among the lanes of one team: the warp when the team fits one, else a named barrier (ids 5..12)
+template <int T>
+__device__ __forceinline__ void team_sync(int team_in_block) {
+  if constexpr (T <= 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(5 + team_in_block), "n"(T) : "memory");
+  }
+}
 
 // SYNC = 0: warps run free.  SYNC = 1: __syncthreads() at the section boundaries.  SYNC >= 2: named barrier
 // among the warps that share a scheduler (warp id mod 4); SYNC = 3 also inside the FIR loop.
@@ -124,21 +143,27 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   return x;
 }
 
-template <int E, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10,
+template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10,
           int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
-  using G = FastGeometry<E, BLOCK>;
-  constexpr int N = G::N, T = G::T, RS = G::RS, WORDS = E / 4;
+  using G = FastGeometry<E, T, BLOCK>;
+  constexpr int N = G::N, RS = G::RS, WORDS = E / 4, W = G::W;
   constexpr int CALLS = (E + 15) / 16;  // Philox calls for E random bytes
   extern __shared__ float4 smem4[];
   const int lane = threadIdx.x & 31;
-  const int t = lane % T;
+  const int t = threadIdx.x % T;
   const int team_in_block = threadIdx.x / T;
+  // linear sample / subcarrier index i lives at row i / E, column i % E; this lane's strided set is
+  // i = t + T m  ->  row (t / E) + W m, column t % E
+  const int tcol = t % E, trow = t / E;
   float2* smem2 = reinterpret_cast<float2*>(smem4);
   float2* buf = smem2 + size_t(team_in_block) * G::TEAM_F2;
   float2* row = buf + t * RS;
   float2* s_tw = smem2 + size_t(G::TEAMS) * G::TEAM_F2;
   float4* s_eq = reinterpret_cast<float4*>(s_tw + G::TW_F2);
+  float* s_red = reinterpret_cast<float*>(s_eq + N) + team_in_block * W;
+  float2* col = buf + trow * RS + tcol;   // strided set: col[W * RS * m]
+  auto tsync = [&]() { team_sync<T>(team_in_block); };
 
   // block-resident copies of the twiddle and equaliser tables
   for (int i = threadIdx.x; i < G::TW_F2; i += BLOCK) s_tw[i] = __ldg(&p.tw[i]);
@@ -202,7 +227,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           if (t == 0) wscr[sym_words] = 0u;
           // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
           replay_prefetch(s + n_teams);
-          __syncwarp();
+          tsync();
 #pragma unroll
           for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
           const unsigned smask = (1u << p.half_bits) - 1u;
@@ -219,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             txc[j] = (txc[j] ^ (txc[j] >> 1)) & p.field_mask;
             txr[j] = (txr[j] ^ (txr[j] >> 1)) & p.field_mask;
           }
-          __syncwarp();
+          tsync();
         } else {
 #pragma unroll
           for (int c = 0; c < CALLS; ++c) {
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             prev[i + 1] = make_float2(q.z, q.w);
           }
         }
-        __syncwarp();
+        tsync();
 #pragma unroll FIR_UNROLL
         for (int c = 0; c < E / 8; ++c) {
           if constexpr (SYNC >= 3) section_sync<SYNC, BLOCK>();
@@ -309,9 +334,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
           for (int i = 0; i < 8; ++i) prev[i] = cur[i];
         }
-        __syncwarp();
+        tsync();
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = buf[m * RS + t];
+        for (int m = 0; m < E; ++m) v[m] = col[W * RS * m];
         if constexpr (REPLAY) {
           // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples (the lines
           // were pulled into L2 one OFDM symbol ago)
@@ -329,38 +354,66 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             }
           }
         }
-        __syncwarp();
+        tsync();
         section_sync<SYNC, BLOCK>();
       }
 
-      // ---- forward FFT of N = E*E points: radix-E in registers, row/column exchange, twiddle, radix-E
+      // ---- forward FFT of N = E*T points: radix-E in registers, row/column exchange, twiddle, radix-E; when the
+      //      team is wider than E a second exchange and a radix-W pass follow (Stockham: natural order throughout)
       fft_dit_inplace<E, -1>(v);
-#ifdef OFDM_SYNC_BEFORE_STORE
-      section_sync<SYNC, BLOCK>();
-#endif
 #pragma unroll
       for (int r = 0; r < E; r += 2) {
         const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
         *reinterpret_cast<float4*>(row + r) = make_float4(a.x, a.y, b.x, b.y);
       }
-      __syncwarp();
+      tsync();
       float2 u[E];
 #pragma unroll
-      for (int m = 0; m < E; ++m) u[m] = buf[m * RS + t];
-      __syncwarp();
-#ifndef OFDM_SYNC_BEFORE_STORE
+      for (int m = 0; m < E; ++m) u[m] = col[W * RS * m];
+      tsync();
       section_sync<SYNC, BLOCK>();
-#endif
 #pragma unroll
-      for (int r = 1; r < E; ++r) u[r] = cmul(u[r], s_tw[(r - 1) * T + t]);
+      for (int r = 1; r < E; ++r) u[r] = cmul(u[r], s_tw[(r - 1) * E + tcol]);
       fft_dit_inplace<E, -1>(u);
+      if constexpr (W > 1) {
+        // pass-2 output r of butterfly j = t lands at linear index E*E*(t/E) + E*r + (t%E); reload the strided
+        // set; radix-W butterflies j = t + T q over the legs u[q + r Q], twiddles W_N^(j r), results in place
+        constexpr int Q = E / W;
+        float2* blk = buf + (E * trow) * RS + tcol;
+#pragma unroll
+        for (int r = 0; r < E; ++r) blk[r * RS] = u[fft_out_index<E>(r)];
+        tsync();
+#pragma unroll
+        for (int m = 0; m < E; ++m) u[m] = col[W * RS * m];
+        const float2* s_tw3 = s_tw + G::TW2_F2;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float2 w1 = s_tw3[t + T * q];
+          if constexpr (W == 2) {
+            const float2 a = u[q], b = cmul(u[q + Q], w1);
+            u[q] = cadd(a, b);
+            u[q + Q] = csub(a, b);
+          } else {
+            const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+            const float2 a0 = u[q], a1 = cmul(u[q + Q], w1), a2 = cmul(u[q + 2 * Q], w2), a3 = cmul(u[q + 3 * Q], w3);
+            const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+            const float2 jd = make_float2(d13.y, -d13.x);   // -j (a1 - a3)
+            u[q] = cadd(s02, s13);
+            u[q + Q] = cadd(d02, jd);
+            u[q + 2 * Q] = csub(s02, s13);
+            u[q + 3 * Q] = csub(d02, jd);
+          }
+        }
+      }
+      // element t + T m of the transform: u[oidx(m)]
+      auto oidx = [](int m) constexpr { return W > 1 ? m : fft_out_index<E>(m); };
 
       if (phase == 0) {
         // ---- x~[t + T m] = swap(u[brev m]); PAPR statistics; publish for the FIR (prefix/models.py:34-44)
         float ssum[4] = {0.f, 0.f, 0.f, 0.f}, smax[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains: latency, not issue
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-          const float2 o = u[fft_out_index<E>(m)];
+          const float2 o = u[oidx(m)];
           const float2 x = make_float2(o.y, o.x);
           if constexpr (PAPR) {
             const float pw = fmaf(x.x, x.x, x.y * x.y);
@@ -368,13 +421,13 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             ssum[m & 3] += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
             smax[m & 3] = fmaxf(smax[m & 3], pw);
           }
-          buf[m * RS + t] = x;
+          col[W * RS * m] = x;
         }
         if (PAPR && active) {
           acc_pow += double((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));
           acc_max = fmaxf(acc_max, fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3])));
         }
-        __syncwarp();
+        tsync();
       } else {
         // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
         //      simulation/models.py:597-606)
@@ -385,14 +438,21 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
         float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
 #pragma unroll
-        for (int off = T / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        for (int off = (T < 32 ? T : 32) / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        if constexpr (W > 1) {
+          if (lane == 0) s_red[trow] = ss;
+          tsync();
+          ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < W; ++i) ss += s_red[i];
+        }
         const float sigma2 = ss * p.mmse_c;
         unsigned rxc[WORDS], rxr[WORDS];
 #pragma unroll
         for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-          const float2 yv = u[fft_out_index<E>(m)];
+          const float2 yv = u[oidx(m)];
           const int k = t + T * m;
           const float4 e = s_eq[k];
           const float a = fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
@@ -451,6 +511,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     return x;
   };
   const unsigned long long b0 = warp_sum64(acc_bit_err), b2 = warp_sum64(acc_sym_err), b3 = warp_sum64(acc_syms);
+  const unsigned long long b4 = warp_sum64(t == 0 ? acc_syms / E : 0ull);   // OFDM symbols: one lane per team counts
   double pw = acc_pow;
   float mx = acc_max;
 #pragma unroll
@@ -463,7 +524,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     if (b3) {
       atomicAdd(&p.counters[CNT_BITS], b3 * (unsigned long long)(2 * p.half_bits));
       atomicAdd(&p.counters[CNT_SYMBOLS], b3);
-      atomicAdd(&p.counters[CNT_OFDM_SYMBOLS], b3 / N);
+      if (b4) atomicAdd(&p.counters[CNT_OFDM_SYMBOLS], b4);
     }
     if (b2) atomicAdd(&p.counters[CNT_SYM_ERRORS], b2);
     if (PAPR) {

@@ -1,19 +1,19 @@
-// One translation unit per team width: nvcc -DOFDM_FAST_E=<8|16|32> -c link_fast_inst.cu
+// One translation unit per team shape: nvcc -DOFDM_FAST_E=<samples per lane> -DOFDM_FAST_T=<lanes per OFDM symbol>
 #include <cstdlib>
 
 #include "link_fast.cuh"
 #include "plan.h"
 
-#ifndef OFDM_FAST_E
-#error "compile with -DOFDM_FAST_E=<lanes per OFDM symbol>"
+#if !defined(OFDM_FAST_E) || !defined(OFDM_FAST_T)
+#error "compile with -DOFDM_FAST_E=<samples per lane> -DOFDM_FAST_T=<lanes per OFDM symbol>"
 #endif
 
 namespace ofdm {
 
-template <int E, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2>
+template <int E, int T, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2>
 static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
-  using G = FastGeometry<E, BLOCK>;
-  auto kern = ofdm_link_fast_kernel<E, DUMP, true, REPLAY, BLOCK, SYNC>;
+  using G = FastGeometry<E, T, BLOCK>;
+  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC>;
   static int occ = 0;   // per process: attribute + occupancy query cost ~0.1 ms each
   if (occ == 0) {
     if (G::SMEM_BYTES > 48 * 1024)
@@ -31,28 +31,23 @@ static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStrea
   return OFDM_OK;
 }
 
-template <int E>
-int launch_fast_width(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
+template <int E, int T>
+int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
 
 template <>
-int launch_fast_width<OFDM_FAST_E>(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream) {
-  constexpr int E = OFDM_FAST_E;
-  if (replay) {
-    if (dump) return launch_fast_kernel<E, true, true>(L, p, stream);
-#if OFDM_FAST_E == 32
-    static const int rvariant = [] { const char* v = std::getenv("OFDM_B200_REPLAY_VARIANT"); return v ? std::atoi(v) : 0; }();
-    if (rvariant == 1) return launch_fast_kernel<E, false, true, 512, 0>(L, p, stream);
-#endif
-    return launch_fast_kernel<E, false, true>(L, p, stream);
-  }
-  if (dump) return launch_fast_kernel<E, true, false>(L, p, stream);
-#if OFDM_FAST_E == 32
-  // OFDM_B200_FAST_VARIANT=4: no cross-warp barriers (the experiment behind profiles/: free-running warps lose
-  // ~3 % to instruction-cache misses)
+int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
+                                                cudaStream_t stream) {
+  constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T;
+  if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
+  if (dump) return launch_fast_kernel<E, T, true, false>(L, p, stream);
+  // One-warp teams: the warps that share a scheduler walk the code in step (named barrier per scheduler, SYNC = 2;
+  // free-running warps lose ~3 % to instruction-cache misses at N = 1024, profiles/).  Multi-warp teams already meet
+  // at their team barriers and lose ~5 % to the extra one (N = 4096), so they run with SYNC = 0.
+  // OFDM_B200_FAST_VARIANT=4 / =2 force SYNC = 0 / 2 for experiments.
   static const int variant = [] { const char* v = std::getenv("OFDM_B200_FAST_VARIANT"); return v ? std::atoi(v) : 0; }();
-  if (variant == 4) return launch_fast_kernel<E, false, false, 512, 0>(L, p, stream);
-#endif
-  return launch_fast_kernel<E, false, false>(L, p, stream);
+  const bool free_running = variant == 4 || (variant != 2 && T > 32);
+  if (free_running) return launch_fast_kernel<E, T, false, false, 512, 0>(L, p, stream);
+  return launch_fast_kernel<E, T, false, false>(L, p, stream);
 }
 
 }  // namespace ofdm

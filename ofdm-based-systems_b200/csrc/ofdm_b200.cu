@@ -119,7 +119,7 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   std::memset(&f, 0, sizeof(f));
   std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
   f.eq_tab = L->d_eq_fast;
-  f.tw = L->d_tw;
+  f.tw = L->d_tw_fast;
   const double snr_lin = std::pow(10.0, snr_db / 10.0);
   // equalization/models.py:43-49 on the unscaled FFT output Y~ = sqrt(N) Y
   f.mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f
@@ -309,6 +309,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
 
   // ---- fast-path eligibility (link_fast.cuh) and its folded tables
   std::vector<float4> eq_fast_host;
+  std::vector<float2> tw_fast_host;
   {
     bool uniform = true;
     for (int k = 1; k < N; ++k) uniform = uniform && (orders[k] == orders[0]);
@@ -316,7 +317,8 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
     L->fast = uniform && !amp && (M == 4 || M == 16 || M == 64 || M == 256) && desc->scheme == OFDM_SCHEME_QAM &&
               desc->modulator == OFDM_MOD_OFDM && desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 &&
-              Lt <= kFastTaps && fast_supports_n(N) && P * P <= N && !(force && force[0] == '1');
+              Lt <= kFastTaps && fast_supports_n(N) && P <= N / fast_samples_per_lane(N) &&
+              !(force && force[0] == '1');
     if (L->fast) {
       L->fixed_order = M;
       const double knorm = std::sqrt(2.0 * (M - 1) / 3.0), sqn = std::sqrt((double)N);
@@ -342,6 +344,19 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
         }
       }
       eq_fast_host.swap(eqf);
+      // twiddles of the fast transform (link_fast.cuh): pass 2 exp(-2 pi i k r / E^2) at [(r-1) E + k], then for
+      // teams wider than E the pass-3 base twiddles exp(-2 pi i j / N), j < N / (T/E)
+      const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
+      for (int r = 1; r < E; ++r)
+        for (int k = 0; k < E; ++k) {
+          const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
+          tw_fast_host.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
+        }
+      if (Wd > 1)
+        for (int j = 0; j < N / Wd; ++j) {
+          const double ang = -2.0 * M_PI * double(j) / double(N);
+          tw_fast_host.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
+        }
     }
   }
 
@@ -352,12 +367,14 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   // one device arena, one host->device copy: [counters | sc | eq | eq_fast | twiddles]
   const std::vector<float2> tw = build_twiddles(N, L->E);
   const size_t off_sc = 256, off_eq = off_sc + N * sizeof(float4), off_eqf = off_eq + N * sizeof(float4),
-               off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), total = off_tw + tw.size() * sizeof(float2);
+               off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), off_twf = off_tw + tw.size() * sizeof(float2),
+               total = off_twf + tw_fast_host.size() * sizeof(float2);
   std::vector<unsigned char> stage(total, 0);
   std::memcpy(stage.data() + off_sc, sc.data(), N * sizeof(float4));
   std::memcpy(stage.data() + off_eq, eq.data(), N * sizeof(float4));
   if (!eq_fast_host.empty()) std::memcpy(stage.data() + off_eqf, eq_fast_host.data(), eq_fast_host.size() * sizeof(float4));
   std::memcpy(stage.data() + off_tw, tw.data(), tw.size() * sizeof(float2));
+  if (!tw_fast_host.empty()) std::memcpy(stage.data() + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
   unsigned char* arena = nullptr;
   CUDA_TRY(cudaMalloc(&arena, total));
   L->arena = arena;
@@ -367,6 +384,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   L->d_eq = reinterpret_cast<float4*>(arena + off_eq);
   L->d_eq_fast = eq_fast_host.empty() ? nullptr : reinterpret_cast<float4*>(arena + off_eqf);
   L->d_tw = reinterpret_cast<float2*>(arena + off_tw);
+  L->d_tw_fast = tw_fast_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_twf);
   L->table_bytes = total;
   *out = L;
   return OFDM_OK;

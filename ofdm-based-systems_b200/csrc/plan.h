@@ -50,6 +50,7 @@ struct ofdm_link {
   int fast = 0;                 // 1 if the fast kernel can run this link in fused mode
   int fixed_order = 0;          // the single QAM order when fast
   float4* d_eq_fast = nullptr;  // decision-domain equaliser table
+  float2* d_tw_fast = nullptr;  // pass-2 twiddles [(r-1)*E + k], then the pass-3 base twiddles exp(-2 pi i j / N)
   float2 taps_fast[8];
   double knorm = 1.0;
 };
@@ -63,6 +64,7 @@ template <int N> int launch_kernel(const ofdm_link* L, const LinkParams& p, cuda
 namespace ofdm {
 struct FastParams;
 bool fast_supports_n(int n);
+int fast_samples_per_lane(int n);
 int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
 }  // namespace ofdm
 

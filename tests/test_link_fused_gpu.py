@@ -14,7 +14,9 @@ CASES = [
     ("headline", 1024, 64, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 20.0, "OFDM", 6),
     ("c1", 64, 4, "QAM", "flat_fading", "CYCLIC", 16, "ZF", 6.0, "OFDM", 64),
     ("c2", 1024, 16, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 16.0, "OFDM", 6),
-    ("c5", 4096, 256, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 30.0, "OFDM", 3),
+    ("c5", 4096, 256, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 30.0, "OFDM", 9),
+    ("n2048", 2048, 64, "QAM", "rayleigh_fading", "CYCLIC", 5, "MMSE", 24.0, "OFDM", 11),
+    ("n2048zf", 2048, 16, "QAM", "severe_multipath", "CYCLIC", 64, "ZF", 14.0, "OFDM", 5),
     ("zp", 256, 16, "QAM", "rayleigh_fading", "ZERO", 5, "MMSE", 15.0, "OFDM", 16),
     ("isi", 128, 64, "QAM", "severe_multipath", "CYCLIC", 2, "ZF", 24.0, "OFDM", 40),
     ("none", 64, 16, "QAM", "Lin-Phoong_P2", "NONE", 0, "MMSE", 22.0, "OFDM", 48),
@@ -47,6 +49,7 @@ def test_fused_dump_replays_through_oracle(case, kat):
     sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
     link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
                 modulator=modulator, equalizer=eq, scheme=scheme)
+    assert link.uses_fast_kernel == (name in ("headline", "c2", "c5", "n2048", "n2048zf"))
     # with inter-symbol interference the oracle's stream must start where the kernel's does (zero history)
     first = 0 if len(taps_raw) - 1 > P else 1000
     res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=first,

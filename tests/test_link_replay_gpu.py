@@ -41,7 +41,8 @@ def rel_err(a, ref):
 
 
 # golden cases whose link shape the register-resident fast kernel covers (csrc/link_fast.cuh)
-FAST_CASES = {"headline_n1024_64qam_mmse", "c2_n1024_16qam_mmse", "c3_n64_64qam_mmse_p2", "c3_n64_64qam_zf_p2"}
+FAST_CASES = {"headline_n1024_64qam_mmse", "c2_n1024_16qam_mmse", "c3_n64_64qam_mmse_p2", "c3_n64_64qam_zf_p2",
+              "c5_n4096_256qam_mmse"}
 
 
 @pytest.mark.parametrize("kernel", ["auto", "general"])
