@@ -6,18 +6,18 @@
 namespace ofdm {
 
 template <int E, int T>
-int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
+int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, cudaStream_t stream);
 
 bool fast_supports_n(int n) { return n == 64 || n == 256 || n == 1024 || n == 2048 || n == 4096; }
 int fast_samples_per_lane(int n) { return n == 64 ? 8 : n == 256 ? 16 : 32; }
 
-int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream) {
+int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, cudaStream_t stream) {
   switch (L->d.n_subcarriers) {
-    case 64: return launch_fast_shape<8, 8>(L, p, dump, replay, stream);
-    case 256: return launch_fast_shape<16, 16>(L, p, dump, replay, stream);
-    case 1024: return launch_fast_shape<32, 32>(L, p, dump, replay, stream);
-    case 2048: return launch_fast_shape<32, 64>(L, p, dump, replay, stream);
-    case 4096: return launch_fast_shape<32, 128>(L, p, dump, replay, stream);
+    case 64: return launch_fast_shape<8, 8>(L, p, dump, replay, adapt, stream);
+    case 256: return launch_fast_shape<16, 16>(L, p, dump, replay, adapt, stream);
+    case 1024: return launch_fast_shape<32, 32>(L, p, dump, replay, adapt, stream);
+    case 2048: return launch_fast_shape<32, 64>(L, p, dump, replay, adapt, stream);
+    case 4096: return launch_fast_shape<32, 128>(L, p, dump, replay, adapt, stream);
     default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", L->d.n_subcarriers);
   }
 }

@@ -58,6 +58,10 @@ struct FastParams {
   // stream, (N + P) samples per OFDM symbol (bits_generation/models.py:27-55, noise/models.py:19-22)
   const unsigned char* bits;
   unsigned long long bits_len;
+  // ADAPT instantiation (per-subcarrier QAM orders, constellation/adaptive.py:52-201):
+  const unsigned int* field_masks;   // [(E/4) * T]: word j of lane t = ((s_k - 1) << 1) in byte i for k = t + T (4 j + i)
+  const float2* level_tab;           // [N]: {g_k, -(2^23 + s_k)} with g_k = 1 / sqrt(2 (M_k - 1) / 3)  (0 when silent);
+                                     // the slicer's s_k - 1 is the 4th component of eq_tab
   const void* noise;        // complex64 (noise_f64 = 0) or complex128 (noise_f64 = 1); NULL = noiseless
   int noise_f64;
 };
@@ -91,11 +95,16 @@ __device__ __forceinline__ void team_sync(int team_in_block) {
 }
 
 // SYNC = 0: warps run free.  SYNC = 1: __syncthreads() at the section boundaries.  SYNC >= 2: named barrier
-// among the warps that share a scheduler (warp id mod 4); SYNC = 3 also inside the FIR loop.
+// among the warps that share a scheduler (warp id mod 4); SYNC = 3 also inside the FIR loop; SYNC = 4: named
+// barrier among groups of 4 consecutive warps (one per scheduler).
 template <int SYNC, int BLOCK>
 __device__ __forceinline__ void section_sync() {
   if constexpr (SYNC == 1) {
     __syncthreads();
+  } else if constexpr (SYNC == 4) {
+    // groups of 4 consecutive warps = one warp per scheduler: every scheduler then hosts warps of BLOCK/128
+    // different groups, which drift into different sections (FMA-heavy, Philox, MUFU) and mix on the pipes
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (threadIdx.x >> 7)), "n"(128) : "memory");
   } else if constexpr (SYNC >= 2) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + ((threadIdx.x >> 5) & 3)), "n"(BLOCK / 4) : "memory");
   }
@@ -143,9 +152,10 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   return x;
 }
 
-template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, int NROUNDS = 10,
-          int FIR_UNROLL = 2>
+template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
+          int NROUNDS = 10, int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+  static_assert(!(ADAPT && REPLAY), "recorded streams with per-subcarrier orders run on the general kernel");
   using G = FastGeometry<E, T, BLOCK>;
   constexpr int N = G::N, RS = G::RS, WORDS = E / 4, W = G::W;
   constexpr int CALLS = (E + 15) / 16;  // Philox calls for E random bytes
@@ -181,6 +191,18 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   unsigned long long acc_bit_err = 0, acc_sym_err = 0, acc_syms = 0;
   double acc_pow = 0.0;
   float acc_max = 0.f;
+
+  // ADAPT: this lane's packed field masks; bits per OFDM symbol carried by its E subcarriers
+  unsigned fmask[ADAPT ? WORDS : 1];
+  unsigned lane_bits = E * 2 * p.half_bits;
+  if constexpr (ADAPT) {
+    lane_bits = 0;
+#pragma unroll
+    for (int j = 0; j < WORDS; ++j) {
+      fmask[j] = __ldg(&p.field_masks[j * T + t]);
+      lane_bits += 2 * __popc(fmask[j]);
+    }
+  }
 
   unsigned next_bits[REPLAY ? WORDS : 1];
   auto replay_prefetch = [&](unsigned long long sn) {
@@ -253,8 +275,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (4 * c + j < WORDS) {
-                txc[4 * c + j] = (ww[j] << 1) & p.field_mask;   // bits 0..3 of each byte -> column index
-                txr[4 * c + j] = (ww[j] >> 3) & p.field_mask;   // bits 4..7 of each byte -> row index
+                const unsigned fm = ADAPT ? fmask[ADAPT ? 4 * c + j : 0] : p.field_mask;
+                txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
+                txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
               }
             }
           }
@@ -266,9 +289,15 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         for (int m = 0; m < E; ++m) {
           const unsigned fc = __byte_perm(txc[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
           const unsigned fr = __byte_perm(txr[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
-          const float li = __uint_as_float(fc) + cen;        // I level:  2*col - (s-1)
-          const float lq = -(__uint_as_float(fr) + cen);     // Q level: (s-1) - 2*row
-          v[m] = make_float2(lq, li);
+          if constexpr (ADAPT) {
+            // per-subcarrier side s_k and power normalisation: (f - (2^23 + s_k)) is the exact integer level
+            const float2 g = __ldg(&p.level_tab[t + T * m]);
+            v[m] = make_float2(-(__uint_as_float(fr) + g.y) * g.x, (__uint_as_float(fc) + g.y) * g.x);
+          } else {
+            const float li = __uint_as_float(fc) + cen;        // I level:  2*col - (s-1)
+            const float lq = -(__uint_as_float(fr) + cen);     // Q level: (s-1) - 2*row
+            v[m] = make_float2(lq, li);
+          }
         }
       } else {
         // ---- channel + noise, in place in shared memory, 8 samples per iteration
@@ -417,11 +446,21 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const float2 x = make_float2(o.y, o.x);
           if constexpr (PAPR) {
             const float pw = fmaf(x.x, x.x, x.y * x.y);
-            // the cyclic prefix repeats the last P <= E samples: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
+            // the cyclic prefix repeats the last P samples; for P <= T: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
             ssum[m & 3] += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
             smax[m & 3] = fmaxf(smax[m & 3], pw);
           }
           col[W * RS * m] = x;
+        }
+        if (PAPR && P > T) {
+          // long prefix (more than one row of samples): the rows above the last one that it also repeats; rolled
+          // loop over this lane's own samples in shared memory (rare shape, keeps the instruction stream small)
+          const int pm = (N - P) / T, pt = (N - P) % T;
+#pragma unroll 1
+          for (int m = pm; m < E - 1; ++m) {
+            const float2 o = col[W * RS * m];
+            if (m > pm || t >= pt) ssum[0] += fmaf(o.x, o.x, o.y * o.y);
+          }
         }
         if (PAPR && active) {
           acc_pow += double((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));
@@ -460,11 +499,13 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const float inv = fast_rcp(e.z + sigma2);
           if constexpr (DUMP) {
             if (active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
-            if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * p.z_unscale, -b * inv * p.z_unscale);
+            const float zu = ADAPT ? 2.f * e.w * __ldg(&p.level_tab[k]).x : p.z_unscale;   // 2 (s_k - 1) / knorm_k
+            if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);
           }
           // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
-          const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), p.slice_top, magic);
-          const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), p.slice_top, magic);
+          const float top = ADAPT ? e.w : p.slice_top;
+          const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
+          const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), top, magic);
           // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
           rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
           rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
@@ -489,8 +530,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
                 const unsigned ct = (txc[j] >> (8 * i + 1)) & 15u, rt = (txr[j] >> (8 * i + 1)) & 15u;
                 const unsigned cr = ((rxc[j] - K) >> (8 * i + 1)) & 15u, rr = ((rxr[j] - K) >> (8 * i + 1)) & 15u;
                 auto ig = [](unsigned x) { x ^= x >> 1; x ^= x >> 2; return x & 15u; };
-                if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((ig(rt) << p.half_bits) | ig(ct));
-                if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rr) << p.half_bits) | ig(cr));
+                const int hb = ADAPT ? __popc((fmask[ADAPT ? j : 0] >> (8 * i)) & 0xffu) : p.half_bits;
+                if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((ig(rt) << hb) | ig(ct));
+                if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rr) << hb) | ig(cr));
               }
             }
           }
@@ -511,6 +553,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     return x;
   };
   const unsigned long long b0 = warp_sum64(acc_bit_err), b2 = warp_sum64(acc_sym_err), b3 = warp_sum64(acc_syms);
+  const unsigned long long bits_total = warp_sum64((acc_syms / E) * lane_bits);
   const unsigned long long b4 = warp_sum64(t == 0 ? acc_syms / E : 0ull);   // OFDM symbols: one lane per team counts
   double pw = acc_pow;
   float mx = acc_max;
@@ -522,7 +565,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   if (lane == 0) {
     if (b0) atomicAdd(&p.counters[CNT_BIT_ERRORS], b0);
     if (b3) {
-      atomicAdd(&p.counters[CNT_BITS], b3 * (unsigned long long)(2 * p.half_bits));
+      atomicAdd(&p.counters[CNT_BITS], bits_total);
       atomicAdd(&p.counters[CNT_SYMBOLS], b3);
       if (b4) atomicAdd(&p.counters[CNT_OFDM_SYMBOLS], b4);
     }

@@ -10,10 +10,10 @@
 
 namespace ofdm {
 
-template <int E, int T, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2>
+template <int E, int T, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2, bool ADAPT = false>
 static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
   using G = FastGeometry<E, T, BLOCK>;
-  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC>;
+  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT>;
   static int occ = 0;   // per process: attribute + occupancy query cost ~0.1 ms each
   if (occ == 0) {
     if (G::SMEM_BYTES > 48 * 1024)
@@ -32,12 +32,18 @@ static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStrea
 }
 
 template <int E, int T>
-int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, cudaStream_t stream);
+int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, cudaStream_t stream);
 
 template <>
 int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
-                                                cudaStream_t stream) {
+                                                bool adapt, cudaStream_t stream) {
   constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T;
+  constexpr int SYNC_DEFAULT = T > 32 ? 0 : 2;
+  if (adapt) {  // per-subcarrier orders (fused mode only)
+    if (replay) return fail(OFDM_EUNSUPPORTED, "replayed streams with per-subcarrier orders run on the general kernel");
+    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, true>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, true>(L, p, stream);
+  }
   if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
   if (dump) return launch_fast_kernel<E, T, true, false>(L, p, stream);
   // One-warp teams: the warps that share a scheduler walk the code in step (named barrier per scheduler, SYNC = 2;
@@ -47,6 +53,9 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   static const int variant = [] { const char* v = std::getenv("OFDM_B200_FAST_VARIANT"); return v ? std::atoi(v) : 0; }();
   const bool free_running = variant == 4 || (variant != 2 && T > 32);
   if (free_running) return launch_fast_kernel<E, T, false, false, 512, 0>(L, p, stream);
+#if OFDM_FAST_T == 32
+  if (variant == 5) return launch_fast_kernel<E, T, false, false, 512, 4>(L, p, stream);
+#endif
   return launch_fast_kernel<E, T, false, false>(L, p, stream);
 }
 

@@ -112,7 +112,7 @@ void set_dump(LinkParams& p, const ofdm_link_dump* d) {
 
 // parameter block of the fast kernel (link_fast.cuh) for one SNR point
 void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link_dump* dump_dev) {
-  const int N = L->d.n_subcarriers, M = L->fixed_order;
+  const int N = L->d.n_subcarriers, M = L->fast == 1 ? L->fixed_order : 1;
   int half_bits = 0;
   while ((1 << (2 * half_bits)) < M) ++half_bits;
   const int side = 1 << half_bits;
@@ -120,6 +120,8 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
   f.eq_tab = L->d_eq_fast;
   f.tw = L->d_tw_fast;
+  f.field_masks = L->d_mask;
+  f.level_tab = L->d_level;
   const double snr_lin = std::pow(10.0, snr_db / 10.0);
   // equalization/models.py:43-49 on the unscaled FFT output Y~ = sqrt(N) Y
   f.mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f
@@ -308,45 +310,64 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   L->mean_h2 = sum_h2 / N;
 
   // ---- fast-path eligibility (link_fast.cuh) and its folded tables
+  //      fast = 1: one QAM order on every subcarrier; fast = 2: per-subcarrier orders (adaptive loading)
   std::vector<float4> eq_fast_host;
-  std::vector<float2> tw_fast_host;
+  std::vector<float2> tw_fast_host, level_host;
+  std::vector<unsigned> mask_host;
   {
-    bool uniform = true;
-    for (int k = 1; k < N; ++k) uniform = uniform && (orders[k] == orders[0]);
-    const int M = orders[0];
+    bool uniform = true, loadable = true;
+    for (int k = 0; k < N; ++k) {
+      const int M = orders[k];
+      uniform = uniform && (M == orders[0]);
+      loadable = loadable && (M == 0 || M == 1 || M == 4 || M == 16 || M == 64 || M == 256);
+    }
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
-    L->fast = uniform && !amp && (M == 4 || M == 16 || M == 64 || M == 256) && desc->scheme == OFDM_SCHEME_QAM &&
-              desc->modulator == OFDM_MOD_OFDM && desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 &&
-              Lt <= kFastTaps && fast_supports_n(N) && P <= N / fast_samples_per_lane(N) &&
-              !(force && force[0] == '1');
+    const bool shape_ok = !amp && desc->scheme == OFDM_SCHEME_QAM && desc->modulator == OFDM_MOD_OFDM &&
+                          desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 && Lt <= kFastTaps && fast_supports_n(N) &&
+                          P < N && !(force && force[0] == '1');
+    L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4) ? 1 : 2;
     if (L->fast) {
-      L->fixed_order = M;
-      const double knorm = std::sqrt(2.0 * (M - 1) / 3.0), sqn = std::sqrt((double)N);
-      L->knorm = knorm;
-      const double tap_scale = 1.0 / (knorm * sqn);   // levels are 2c-(s-1) = k * point; unnormalised IFFT
+      const double sqn = std::sqrt((double)N);
+      L->fixed_order = L->fast == 1 ? orders[0] : 0;
+      // levels are 2c-(s-1) = knorm * point and the IFFT is unnormalised: with one order the taps absorb
+      // 1/(knorm sqrt N); with per-subcarrier orders 1/knorm_k is applied at the mapper (level_tab)
+      L->knorm = L->fast == 1 ? std::sqrt(2.0 * (orders[0] - 1) / 3.0) : 1.0;
+      const double tap_scale = 1.0 / (L->knorm * sqn);
       for (int l = 0; l < kFastTaps; ++l)
         L->taps_fast[l] = l < Lt ? make_float2((float)(taps_chan[2 * l] * tap_scale), (float)(taps_chan[2 * l + 1] * tap_scale))
                                  : make_float2(0.f, 0.f);
       // decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1):  k/2 (slicer), 1/sqrt(N) (receiver FFT)
-      // and 1/(s-1) (unit interval for FFMA.SAT) folded into A
-      int side = 1;
-      while (side * side < M) side *= 2;
-      const double dec = knorm / (2.0 * sqn * (side - 1));
+      // and 1/(s-1) (unit interval for FFMA.SAT) folded into A; 4th component = s-1
       std::vector<float4> eqf(N);
+      const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
+      level_host.assign(N, make_float2(0.f, -8388609.0f));
+      mask_host.assign(size_t(E / 4) * T, 0u);
       for (int k = 0; k < N; ++k) {
+        const int M = orders[k] < 4 ? 1 : orders[k];
+        int side = 1;
+        while (side * side < M) side *= 2;
+        const double knorm_k = std::sqrt(2.0 * (M - 1) / 3.0);
+        const float top = float(side - 1);
         const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
-        if (desc->equalizer == OFDM_EQ_NONE) {
-          eqf[k] = make_float4((float)dec, 0.f, 1.f, 0.f);
-        } else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) {
-          eqf[k] = make_float4((float)(dec * 1e10), 0.f, 1.f, 0.f);   // equalization/models.py:33-35: h := 1e-10
+        if (side == 1) {
+          eqf[k] = make_float4(0.f, 0.f, 1.f, 0.f);   // silent subcarrier: decision index 0, no errors counted
         } else {
-          eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), 0.f);
+          const double dec = knorm_k / (2.0 * sqn * (side - 1));
+          if (desc->equalizer == OFDM_EQ_NONE) {
+            eqf[k] = make_float4((float)dec, 0.f, 1.f, top);
+          } else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) {
+            eqf[k] = make_float4((float)(dec * 1e10), 0.f, 1.f, top);   // equalization/models.py:33-35: h := 1e-10
+          } else {
+            eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), top);
+          }
+          level_host[k] = make_float2((float)(1.0 / knorm_k), -(8388608.0f + float(side)));
+          const int t = k % T, m = k / T;
+          mask_host[size_t(m / 4) * T + t] |= (unsigned)((side - 1) << 1) << (8 * (m % 4));
         }
       }
       eq_fast_host.swap(eqf);
       // twiddles of the fast transform (link_fast.cuh): pass 2 exp(-2 pi i k r / E^2) at [(r-1) E + k], then for
       // teams wider than E the pass-3 base twiddles exp(-2 pi i j / N), j < N / (T/E)
-      const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
       for (int r = 1; r < E; ++r)
         for (int k = 0; k < E; ++k) {
           const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
@@ -357,6 +378,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
           const double ang = -2.0 * M_PI * double(j) / double(N);
           tw_fast_host.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
         }
+      if (L->fast == 1) { level_host.clear(); mask_host.clear(); }
     }
   }
 
@@ -368,13 +390,16 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   const std::vector<float2> tw = build_twiddles(N, L->E);
   const size_t off_sc = 256, off_eq = off_sc + N * sizeof(float4), off_eqf = off_eq + N * sizeof(float4),
                off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), off_twf = off_tw + tw.size() * sizeof(float2),
-               total = off_twf + tw_fast_host.size() * sizeof(float2);
+               off_lvl = off_twf + tw_fast_host.size() * sizeof(float2), off_msk = off_lvl + level_host.size() * sizeof(float2),
+               total = off_msk + mask_host.size() * sizeof(unsigned);
   std::vector<unsigned char> stage(total, 0);
   std::memcpy(stage.data() + off_sc, sc.data(), N * sizeof(float4));
   std::memcpy(stage.data() + off_eq, eq.data(), N * sizeof(float4));
   if (!eq_fast_host.empty()) std::memcpy(stage.data() + off_eqf, eq_fast_host.data(), eq_fast_host.size() * sizeof(float4));
   std::memcpy(stage.data() + off_tw, tw.data(), tw.size() * sizeof(float2));
   if (!tw_fast_host.empty()) std::memcpy(stage.data() + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
+  if (!level_host.empty()) std::memcpy(stage.data() + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
+  if (!mask_host.empty()) std::memcpy(stage.data() + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
   unsigned char* arena = nullptr;
   CUDA_TRY(cudaMalloc(&arena, total));
   L->arena = arena;
@@ -385,6 +410,8 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   L->d_eq_fast = eq_fast_host.empty() ? nullptr : reinterpret_cast<float4*>(arena + off_eqf);
   L->d_tw = reinterpret_cast<float2*>(arena + off_tw);
   L->d_tw_fast = tw_fast_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_twf);
+  L->d_level = level_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_lvl);
+  L->d_mask = mask_host.empty() ? nullptr : reinterpret_cast<unsigned*>(arena + off_msk);
   L->table_bytes = total;
   *out = L;
   return OFDM_OK;
@@ -398,7 +425,7 @@ void ofdm_link_destroy(ofdm_link* L) {
 }
 
 int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* L) { return L ? L->bits_per_ofdm : OFDM_EINVAL; }
-int ofdm_link_uses_fast_kernel(const ofdm_link* L) { return L ? L->fast : OFDM_EINVAL; }
+int ofdm_link_uses_fast_kernel(const ofdm_link* L) { return L ? (L->fast != 0) : OFDM_EINVAL; }
 uint64_t ofdm_link_table_bytes(const ofdm_link* L) { return L ? L->table_bytes : 0; }
 void* ofdm_link_counters_device_ptr(ofdm_link* L) { return L ? (void*)L->d_cnt : nullptr; }
 
@@ -429,7 +456,7 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     f.point = point;
     f.sym_begin = first_symbol;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, false, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);
@@ -454,7 +481,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
   if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
   DeviceGuard guard(L->device);
   const uint64_t whole = n_symbols * (uint64_t)L->bits_per_ofdm;
-  if (L->fast && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
+  if (L->fast == 1 && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
       (reinterpret_cast<uintptr_t>(bits_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(noise_dev) & 15) == 0) {
     // common link shape, whole OFDM symbols: the fast kernel streams the recorded bits and noise
     FastParams f;
@@ -464,7 +491,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
     f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
     f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, true, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, true, false, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);

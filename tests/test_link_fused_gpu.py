@@ -49,7 +49,7 @@ def test_fused_dump_replays_through_oracle(case, kat):
     sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
     link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
                 modulator=modulator, equalizer=eq, scheme=scheme)
-    assert link.uses_fast_kernel == (name in ("headline", "c2", "c5", "n2048", "n2048zf"))
+    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf"))
     # with inter-symbol interference the oracle's stream must start where the kernel's does (zero history)
     first = 0 if len(taps_raw) - 1 > P else 1000
     res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=first,
@@ -66,6 +66,55 @@ def test_fused_dump_replays_through_oracle(case, kat):
         assert res.bit_errors == ref["bit_errors"]
         assert res.symbol_errors == ref["symbol_errors"]
     assert res.bits == n_ofdm * n * bps
+    assert abs(res.papr_db - ref["papr_db"]) < 2e-4
+    link.close()
+
+
+ADAPTIVE_CASES = [
+    # name, N, channel, P, eq, snr, n_ofdm, expects the fast kernel
+    ("a64", 64, "Lin-Phoong_P1", 3, "MMSE", 24.0, 48, True),
+    ("a256", 256, "severe_multipath", 7, "ZF", 26.0, 24, True),
+    ("a1024", 1024, "severe_multipath", 7, "MMSE", 22.0, 8, True),
+    ("a4096", 4096, "rayleigh_fading", 5, "MMSE", 28.0, 8, True),
+    ("a128", 128, "two_ray", 1, "MMSE", 20.0, 32, False),
+]
+
+
+@pytest.mark.parametrize("case", ADAPTIVE_CASES, ids=[c[0] for c in ADAPTIVE_CASES])
+def test_fused_adaptive_loading_replays_through_oracle(case, kat):
+    """Per-subcarrier QAM orders (0 / 4 / 16 / 64 / 256, constellation/adaptive.py:52-201): the kernel's own bits
+    and noise, replayed through the reference algorithm, give the same decisions and counts."""
+    from ofdm_based_systems._native import Link
+    name, n, chan, P, eq, snr, n_ofdm, fast = case
+    rng = np.random.default_rng(n)
+    orders = rng.choice([0, 4, 16, 64, 256], size=n, p=[0.15, 0.25, 0.25, 0.2, 0.15]).astype(np.int64)
+    orders[:5] = [256, 0, 4, 64, 16]
+    taps_raw = kat["chan_" + chan]
+    setup = oc.LinkSetup(n_sc=n, taps_raw=taps_raw, snr_db=snr, order=16, eq=eq, orders=orders, prefix_len_override=P)
+    active_frac = float(np.mean(orders > 1))
+    sigma = float(np.sqrt(active_frac / 10 ** (snr / 10) / 2))
+    link = Link(n, setup.taps_chan, setup.H_eq, orders, prefix_type="CYCLIC", prefix_len=P, equalizer=eq)
+    assert link.uses_fast_kernel == fast
+    bps = [oc.bits_per_symbol(int(o)) if o > 1 else 0 for o in orders]
+    assert link.bits_per_ofdm_symbol == sum(bps)
+    res, d = link.run_fused(snr, sigma, n_ofdm, seed=77, point=2, first_symbol=123456789012,
+                            dump=("z", "rx_labels", "tx_labels", "noise"))
+    tx_bytes = pack_labels(d["tx_labels"], bps)
+    ref = oc.run_link(setup, tx_bytes, n_ofdm * sum(bps), noise=d["noise"].astype(np.complex128).reshape(-1))
+    act = orders > 1
+    assert np.all(d["tx_labels"][:, ~act] == 0) and np.all(d["rx_labels"][:, ~act] == 0)
+    z_ref = np.asarray(ref["received_symbols"]).reshape(n_ofdm, n)
+    assert np.max(np.abs(d["z"][:, act] - z_ref[:, act])) / np.max(np.abs(z_ref[:, act])) < 1e-5
+    rx_ref = np.asarray(ref["rx_labels"]).reshape(n_ofdm, n)
+    dist = np.full(z_ref.shape, np.inf)
+    for k in np.nonzero(act)[0]:
+        dist[:, k] = oc.qam_boundary_distance(z_ref[:, k], int(orders[k]))
+    mismatch = (d["rx_labels"] != np.where(act, rx_ref, 0)) & act
+    assert not np.any(mismatch & (dist > 2e-4))
+    if not mismatch.any():
+        assert res.bit_errors == ref["bit_errors"]
+        assert res.symbol_errors == ref["symbol_errors"]
+    assert res.bits == n_ofdm * sum(bps) and res.symbols == n_ofdm * n
     assert abs(res.papr_db - ref["papr_db"]) < 2e-4
     link.close()
 
