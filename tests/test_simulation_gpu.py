@@ -131,3 +131,26 @@ def test_sweep_points_are_independent_and_ordered(kat):
     again = sweep.sweep([20.0], 4000, seed=5)[0]
     assert again["bit_errors"] != res[3]["bit_errors"]            # point index is part of the Philox counter
     sweep.close()
+
+
+# docs/OFDM-Based Systems.tex:246-264 (the reference's only published numbers for this path): BER at 30 dB,
+# Lin-Phoong P2 (4 taps), N = 64, 64-QAM, MMSE, prefix_length_ratio 0.34 / 0.68 / 1.00 / 1.34 -> 1..4 guard samples.
+# Lengths 1 and 2 are shorter than the channel memory (inter-symbol interference).
+PUBLISHED_MMSE_30DB = {("CYCLIC", 1): 0.0410, ("CYCLIC", 2): 0.0266, ("CYCLIC", 3): 0.0189, ("CYCLIC", 4): 0.0189,
+                       ("ZERO", 1): 0.0411, ("ZERO", 2): 0.0268, ("ZERO", 3): 0.0190, ("ZERO", 4): 0.0190}
+
+
+@pytest.mark.parametrize("prefix,ratio", [(p, r) for p in ("CYCLIC", "ZERO") for r in (0.34, 0.68, 1.00, 1.34)])
+def test_published_short_prefix_table(prefix, ratio, kat):
+    """The published table was measured on 6e6 bits per point (binomial s.e. ~6e-5, larger with the per-symbol
+    correlation) and is printed to 4 decimals; 3e7 bits here.  Tolerance 1e-3 absolute (5 % of the value)."""
+    from ofdm_based_systems.simulation.sweep import LinkConfig, LinkSweep
+    taps = kat["chan_Lin-Phoong_P2"]
+    P = int(ratio * (len(taps) - 1))                       # simulation/models.py:251-253
+    cfg = LinkConfig(num_subcarriers=64, taps_raw=taps, constellation_order=64, prefix_scheme=prefix, prefix_length=P,
+                     equalizator_type="MMSE")
+    sweep = LinkSweep(cfg)
+    got = sweep.sweep([30.0], 80_000, seed=11)[0]
+    sweep.close()
+    assert got["total_bits"] == 80_000 * 384
+    assert abs(got["bit_error_rate"] - PUBLISHED_MMSE_30DB[(prefix, P)]) < 1e-3, (P, got["bit_error_rate"])
