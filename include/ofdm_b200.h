@@ -138,16 +138,22 @@ typedef struct ofdm_waterfill_desc {
   double total_power;    /* N in adaptive mode, 1.0 in fixed mode (simulation/models.py:297, 486)         */
   double gap;            /* QAM: Qinv(ser/4)^2 / 3;  PSK: Qinv(ser/2)^2 / (2 pi^2)   (caller: scipy norm.isf) */
   double tolerance;      /* bisection stop, default 1e-8                                                  */
+  int32_t order_rule;    /* 0: gap rule above; 1: Shannon capacity rule, calculate_constellation_orders
+                            (constellation/adaptive.py:271-329) with min_order / max_order always applied  */
+  int32_t reserved;
+  double capacity_scaling; /* order_rule 1: bits = capacity * capacity_scaling (JSON capacity_scaling_factor) */
 } ofdm_waterfill_desc;
 /* taps: [n][n_taps] complex128 RAW taps; outputs power [n][N] f64, orders [n][N] i32, water_level [n] f64 (NaN
- * when uniform), optional h_eq [n][N] complex128 and iterations [n] i32.  HOST buffers, synchronous. */
+ * when uniform), optional h_eq [n][N] complex128, iterations [n] i32 and capacity [n][N] f64 = log2(1 + P g / N0
+ * + 1e-12) per subcarrier (calculate_capacity, power_allocation/models.py:262-294; summed over a row it is what
+ * compare_allocations :296-334 compares).  HOST buffers, synchronous. */
 int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* desc, const double* taps, int64_t n_realisations,
                                    double* power, int32_t* orders, double* water_level, double* h_eq,
-                                   int32_t* iterations);
+                                   int32_t* iterations, double* capacity);
 /* same on DEVICE buffers, asynchronous on `stream` */
 int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* desc, const double* taps_dev, int64_t n_realisations,
                                        double* power_dev, int32_t* orders_dev, double* water_level_dev,
-                                       double* h_eq_dev, int32_t* iterations_dev, void* stream);
+                                       double* h_eq_dev, int32_t* iterations_dev, double* capacity_dev, void* stream);
 
 /* FP32 FFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per FFMA) on the current device,
  * the roofline denominator SURVEY 8(d) asks for; <0 on error. */

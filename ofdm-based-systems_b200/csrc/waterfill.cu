@@ -4,6 +4,8 @@
 //   P_k = max(0, mu - floor_k) rescaled to the budget       power_allocation/models.py:165-176
 //   reported water level = mean(P_k + N0/g_k | P_k > 1e-10) simulation/models.py:311-313
 //   gap-rule constellation order per subcarrier             constellation/models.py:297-321 (QAM), 459-474 (PSK)
+//   or the Shannon-capacity rule                            constellation/adaptive.py:271-329
+//   capacity per subcarrier log2(1 + P g / N0 + 1e-12)      power_allocation/models.py:262-294
 // All arithmetic in fp64 (the reference is fp64 and the order decision is a rounding of log2(1 + snr/gap)).
 #include <cmath>
 #include <cstring>
@@ -22,8 +24,9 @@ struct WaterfillParams {
   int* orders;           // [F][N]
   double* water_level;   // [F]   (NaN when not water-filling)
   int* iterations;       // [F]   bisection steps used (may be null)
-  int n, n_taps, scheme, waterfilling, min_order, max_order;
-  double noise_power, total_power, gap, tolerance, ser;
+  double* capacity;      // [F][N] (may be null)
+  int n, n_taps, scheme, waterfilling, min_order, max_order, order_rule;
+  double noise_power, total_power, gap, tolerance, ser, capacity_scaling;
 };
 
 __device__ __forceinline__ double block_sum(double x, double* scratch) {
@@ -66,6 +69,15 @@ __device__ __forceinline__ double2 channel_response(const double2* taps, int n_t
 }
 
 __device__ __forceinline__ int gap_rule_order(double snr, const WaterfillParams& p) {
+  if (p.order_rule == 1) {
+    // calculate_constellation_orders: bits = clip(capacity * scaling, 0, log2 max); QAM: floor to even, PSK: floor;
+    // below log2 min -> nothing transmitted
+    const double cap = log2(1.0 + snr + 1e-12);
+    double b = fmin(fmax(cap * p.capacity_scaling, 0.0), log2((double)p.max_order));
+    b = p.scheme == 0 ? floor(b / 2.0) * 2.0 : floor(b);
+    if (b < log2((double)p.min_order) || b <= 0.0) return 0;
+    return 1 << (int)b;
+  }
   int bits;
   if (p.scheme == 0) {  // QAM: round-half-even of log2(1 + snr/gap), made even
     bits = (int)rint(log2(1.0 + snr / p.gap));
@@ -133,6 +145,7 @@ __global__ void __launch_bounds__(kWfThreads) waterfill_bitload_kernel(const Wat
       const double g = h.x * h.x + h.y * h.y;
       if (pk > 1e-10) { lvl += pk + p.noise_power / g; cnt += 1.0; }
       orders[k] = gap_rule_order(pk * g / p.noise_power, p);
+      if (p.capacity) p.capacity[(size_t)f * n + k] = log2(1.0 + pk * g / p.noise_power + 1e-12);
     }
     lvl = block_sum(lvl, scratch);
     cnt = block_sum(cnt, scratch);
@@ -144,6 +157,7 @@ __global__ void __launch_bounds__(kWfThreads) waterfill_bitload_kernel(const Wat
       const double g = h.x * h.x + h.y * h.y;
       power[k] = pk;
       orders[k] = gap_rule_order(pk * g / p.noise_power, p);
+      if (p.capacity) p.capacity[(size_t)f * n + k] = log2(1.0 + pk * g / p.noise_power + 1e-12);
     }
     if (threadIdx.x == 0) p.water_level[f] = nan("");
   }
@@ -158,10 +172,13 @@ extern "C" {
 
 int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* d, const double* taps_dev, int64_t n_realisations,
                                        double* power_dev, int32_t* orders_dev, double* water_level_dev,
-                                       double* h_eq_dev, int32_t* iterations_dev, void* stream) {
+                                       double* h_eq_dev, int32_t* iterations_dev, double* capacity_dev, void* stream) {
   if (!d || !taps_dev || !power_dev || !orders_dev || !water_level_dev) return fail(OFDM_EINVAL, "null argument");
   if (d->n_subcarriers < 1 || d->n_taps < 1 || d->n_taps > kMaxTaps) return fail(OFDM_EINVAL, "bad n_subcarriers / n_taps");
   if (d->total_power < 0) return fail(OFDM_EINVAL, "Total power must be non-negative, got %g", d->total_power);
+  if (d->order_rule != 0 && d->order_rule != 1) return fail(OFDM_EINVAL, "order_rule=%d", d->order_rule);
+  if (d->order_rule == 1 && (d->min_order < 2 || d->max_order < d->min_order))
+    return fail(OFDM_EINVAL, "the capacity rule needs 2 <= min_order <= max_order");
   if (n_realisations <= 0) return OFDM_OK;
   WaterfillParams p;
   p.taps = reinterpret_cast<const double2*>(taps_dev);
@@ -170,6 +187,9 @@ int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* d, const doubl
   p.orders = orders_dev;
   p.water_level = water_level_dev;
   p.iterations = iterations_dev;
+  p.capacity = capacity_dev;
+  p.order_rule = d->order_rule;
+  p.capacity_scaling = d->capacity_scaling;
   p.n = d->n_subcarriers;
   p.n_taps = d->n_taps;
   p.scheme = d->scheme;
@@ -189,7 +209,7 @@ int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* d, const doubl
 
 int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* d, const double* taps, int64_t n_realisations,
                                    double* power, int32_t* orders, double* water_level, double* h_eq,
-                                   int32_t* iterations) {
+                                   int32_t* iterations, double* capacity) {
   if (!d || !taps || !power || !orders || !water_level) return fail(OFDM_EINVAL, "null argument");
   const size_t F = (size_t)n_realisations, N = (size_t)d->n_subcarriers, L = (size_t)d->n_taps;
   if (F == 0) return OFDM_OK;
@@ -197,7 +217,7 @@ int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* d, const double* t
   auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };   // double2 accesses need 16-byte alignment
   const size_t o_taps = 0, o_pow = up16(o_taps + F * L * 16), o_ord = up16(o_pow + F * N * 8),
                o_lvl = up16(o_ord + F * N * 4), o_heq = up16(o_lvl + F * 8), o_it = up16(o_heq + (h_eq ? F * N * 16 : 0)),
-               total = o_it + F * 4;
+               o_cap = up16(o_it + F * 4), total = o_cap + (capacity ? F * N * 8 : 0);
   CUDA_TRY(cudaMalloc(&arena, total));
   int rc = OFDM_OK;
   cudaError_t e = cudaMemcpy(arena + o_taps, taps, F * L * 16, cudaMemcpyHostToDevice);
@@ -207,7 +227,8 @@ int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* d, const double* t
                                             reinterpret_cast<double*>(arena + o_pow), reinterpret_cast<int32_t*>(arena + o_ord),
                                             reinterpret_cast<double*>(arena + o_lvl),
                                             h_eq ? reinterpret_cast<double*>(arena + o_heq) : nullptr,
-                                            reinterpret_cast<int32_t*>(arena + o_it), nullptr);
+                                            reinterpret_cast<int32_t*>(arena + o_it),
+                                            capacity ? reinterpret_cast<double*>(arena + o_cap) : nullptr, nullptr);
   auto back = [&](void* dst, size_t off, size_t bytes) {
     if (rc || !dst) return;
     cudaError_t ee = cudaMemcpy(dst, arena + off, bytes, cudaMemcpyDeviceToHost);
@@ -218,6 +239,7 @@ int ofdm_waterfill_bitload_batched(const ofdm_waterfill_desc* d, const double* t
   back(water_level, o_lvl, F * 8);
   back(h_eq, o_heq, F * N * 16);
   back(iterations, o_it, F * 4);
+  back(capacity, o_cap, F * N * 8);
   cudaFree(arena);
   return rc;
 }

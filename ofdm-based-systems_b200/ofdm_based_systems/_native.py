@@ -42,7 +42,8 @@ class LinkResult(C.Structure):
 class WaterfillDesc(C.Structure):
     _fields_ = [("n_subcarriers", C.c_int32), ("n_taps", C.c_int32), ("scheme", C.c_int32), ("waterfilling", C.c_int32),
                 ("min_order", C.c_int32), ("max_order", C.c_int32), ("snr_db", C.c_double), ("total_power", C.c_double),
-                ("gap", C.c_double), ("tolerance", C.c_double)]
+                ("gap", C.c_double), ("tolerance", C.c_double), ("order_rule", C.c_int32), ("reserved", C.c_int32),
+                ("capacity_scaling", C.c_double)]
 
 
 class LinkDump(C.Structure):
@@ -88,8 +89,8 @@ def _load() -> C.CDLL:
     lib.ofdm_link_read_result.argtypes = [vp, vp, C.POINTER(LinkResult)]
     lib.ofdm_link_counters_device_ptr.argtypes = [vp]
     lib.ofdm_link_counters_device_ptr.restype = vp
-    lib.ofdm_waterfill_bitload_batched.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp]
-    lib.ofdm_waterfill_bitload_batched_dev.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp]
+    lib.ofdm_waterfill_bitload_batched.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp]
+    lib.ofdm_waterfill_bitload_batched_dev.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
     if lib.ofdm_b200_abi_version() != 1:
         raise NativeLibraryMissing(f"{LIB_PATH}: ABI version {lib.ofdm_b200_abi_version()} != 1, rebuild it")
     return lib
@@ -263,24 +264,39 @@ def bit_loading_gap(ser: float, scheme: str = "QAM") -> float:
 
 def waterfill_bitload_batched(taps: np.ndarray, n_subcarriers: int, snr_db: float, *, ser: float = 1e-3,
                               total_power: Optional[float] = None, scheme: str = "QAM", waterfilling: bool = True,
-                              min_order: int = 0, max_order: int = 0, tolerance: float = 1e-8):
-    """Power allocation + gap-rule orders for a batch of channel realisations on the GPU.
-    taps: [F, L] complex RAW taps.  Returns dict(power [F,N], orders [F,N], water_level [F], h_eq [F,N],
-    iterations [F])."""
+                              min_order: int = 0, max_order: int = 0, tolerance: float = 1e-8,
+                              order_rule: str = "gap", capacity_scaling: float = 1.0):
+    """Power allocation + constellation orders for a batch of channel realisations on the GPU.
+    taps: [F, L] complex RAW taps.  order_rule "gap" = calculate_bit_loading_order (constellation/models.py:297-321,
+    459-474); "capacity" = calculate_constellation_orders (constellation/adaptive.py:271-329, needs min / max order).
+    Returns dict(power [F,N], orders [F,N], water_level [F], h_eq [F,N], iterations [F], capacity [F,N])."""
     require_gpu()
     taps = np.ascontiguousarray(np.atleast_2d(taps), dtype=np.complex128)
     f, l = taps.shape
     n = int(n_subcarriers)
     desc = WaterfillDesc(n, l, SCHEME[scheme], int(bool(waterfilling)), int(min_order), int(max_order), float(snr_db),
-                         float(n if total_power is None else total_power), bit_loading_gap(ser, scheme), float(tolerance))
+                         float(n if total_power is None else total_power), bit_loading_gap(ser, scheme), float(tolerance),
+                         {"gap": 0, "capacity": 1}[order_rule], 0, float(capacity_scaling))
     power = np.empty((f, n), dtype=np.float64)
     orders = np.empty((f, n), dtype=np.int32)
     level = np.empty(f, dtype=np.float64)
     h_eq = np.empty((f, n), dtype=np.complex128)
     iters = np.empty(f, dtype=np.int32)
+    cap = np.empty((f, n), dtype=np.float64)
     _check(lib.ofdm_waterfill_bitload_batched(C.byref(desc), taps.ctypes.data, f, power.ctypes.data, orders.ctypes.data,
-                                              level.ctypes.data, h_eq.ctypes.data, iters.ctypes.data))
-    return dict(power=power, orders=orders.astype(np.int64), water_level=level, h_eq=h_eq, iterations=iters)
+                                              level.ctypes.data, h_eq.ctypes.data, iters.ctypes.data, cap.ctypes.data))
+    return dict(power=power, orders=orders.astype(np.int64), water_level=level, h_eq=h_eq, iterations=iters,
+                capacity=cap)
+
+
+def compare_allocations_batched(taps: np.ndarray, n_subcarriers: int, snr_db: float, *, total_power: float = 1.0):
+    """compare_allocations (power_allocation/models.py:296-334) for a batch of channel realisations: uniform vs
+    water-filling capacity, summed over the subcarriers of each realisation."""
+    uni = waterfill_bitload_batched(taps, n_subcarriers, snr_db, total_power=total_power, waterfilling=False)
+    wf = waterfill_bitload_batched(taps, n_subcarriers, snr_db, total_power=total_power, waterfilling=True)
+    cu, cw = uni["capacity"].sum(axis=1), wf["capacity"].sum(axis=1)
+    return {"uniform_capacity": cu, "waterfilling_capacity": cw, "capacity_gain": cw - cu,
+            "capacity_gain_percent": np.where(cu > 0, 100 * (cw - cu) / np.where(cu > 0, cu, 1), 0.0)}
 
 
 def measure_fp32_tflops(iters: int = 4096) -> float:

@@ -52,3 +52,33 @@ def test_known_answers():
     assert out["iterations"][0] <= 100
     with pytest.raises(ValueError):
         waterfill_bitload_batched(np.array([[1.0 + 0j]]), 64, 10.0, total_power=-1.0)
+
+
+def test_capacity_rule_and_allocation_comparison_match_oracle():
+    """calculate_constellation_orders (constellation/adaptive.py:271-329) and compare_allocations
+    (power_allocation/models.py:296-334) as batched rules of the same kernel."""
+    from ofdm_based_systems._native import compare_allocations_batched, waterfill_bitload_batched
+    rng = np.random.default_rng(7)
+    f, l, n, snr = 64, 6, 128, 16.0
+    taps = (rng.normal(size=(f, l)) + 1j * rng.normal(size=(f, l))) * np.sqrt(np.exp(-np.arange(l) / 2))
+    n0 = 10 ** (-snr / 10)
+    for scheme, scaling in (("QAM", 1.0), ("QAM", 0.75), ("PSK", 0.5)):
+        out = waterfill_bitload_batched(taps, n, snr, scheme=scheme, order_rule="capacity", capacity_scaling=scaling,
+                                        min_order=4, max_order=256)
+        mism = 0
+        for i in range(f):
+            gains = np.abs(np.fft.fft(taps[i], n)) ** 2
+            power = oc.waterfilling(float(n), gains, n0)
+            cap = oc.capacity_per_subcarrier(power, gains, n0)
+            np.testing.assert_allclose(out["capacity"][i], cap, rtol=1e-9, atol=1e-12)
+            mism += int(np.sum(out["orders"][i] != oc.shannon_orders(cap, 4, 256, scaling, scheme)))
+        assert mism <= 2          # floor() of a value within 1e-9 of an integer
+    cmp_ = compare_allocations_batched(taps, n, snr, total_power=1.0)
+    for i in range(0, f, 7):
+        gains = np.abs(np.fft.fft(taps[i], n)) ** 2
+        wf = oc.waterfilling(1.0, gains, n0)
+        cu, cw = oc.capacity(oc.uniform_power(1.0, n), gains, n0), oc.capacity(wf, gains, n0)
+        assert abs(cmp_["uniform_capacity"][i] - cu) < 1e-8 * cu and abs(cmp_["waterfilling_capacity"][i] - cw) < 1e-7 * cw
+    assert np.all(cmp_["capacity_gain"] > -1e-9)
+    with pytest.raises(ValueError):
+        waterfill_bitload_batched(taps, n, snr, order_rule="capacity")          # needs min / max order
