@@ -155,6 +155,34 @@ int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* desc, const do
                                        double* power_dev, int32_t* orders_dev, double* water_level_dev,
                                        double* h_eq_dev, int32_t* iterations_dev, double* capacity_dev, void* stream);
 
+/* Frame batches: `n_frames` channel realisations, `symbols_per_frame` OFDM symbols each, in one launch of the link
+ * kernel (what the reference would run as one Simulation per realisation, simulation/models.py:155-212, :454-606).
+ * OFDM modulator, QAM, cyclic prefix >= channel memory, <= 8 taps, N in {64, 256, 1024, 2048, 4096}. */
+typedef struct ofdm_frames_desc {
+  int32_t n_subcarriers;
+  int32_t prefix_len;
+  int32_t equalizer;     /* OFDM_EQ_*                                                                          */
+  int32_t n_taps;
+  int32_t loading;       /* 0: fixed_order on every subcarrier; 1: per-frame gap-rule orders (adaptive mode,
+                            simulation/models.py:277-352), bounded by min_order / max_order (max_order <= 256)  */
+  int32_t fixed_order;   /* 4, 16, 64 or 256                                                                    */
+  int32_t waterfilling;  /* loading 1: power fed to the gap rule, 1 = water-filling, 0 = uniform                */
+  int32_t min_order;
+  int32_t max_order;
+  int32_t device;        /* CUDA device ordinal, -1 = current                                                   */
+  double snr_db;
+  double gap;            /* QAM gap Qinv(ser/4)^2 / 3 (loading 1)                                               */
+} ofdm_frames_desc;
+/* taps: [n_frames][n_taps] complex128 RAW taps (HOST), or NULL = a fresh Rayleigh realisation per frame drawn on the
+ * device (examples/generate_channel_models.py:70-78: CN(0,1) sqrt(exp(-l/2)), unit energy) from Philox keyed by `seed`
+ * with the global frame index first_frame + f.  OFDM symbol s of frame f uses the Philox counters of global symbol
+ * (first_frame + f) * symbols_per_frame + s, so frames shard over GPUs like symbols do.
+ * Outputs (HOST): total (sums; tx_power_max is the maximum), optional per_frame [n_frames], orders [n_frames][N] the
+ * links ran with, taps_out [n_frames][n_taps] complex128. */
+int ofdm_frames_run(const ofdm_frames_desc* desc, const double* taps, int64_t n_frames, uint64_t symbols_per_frame,
+                    uint64_t seed, uint32_t point, uint64_t first_frame, ofdm_link_result* total,
+                    ofdm_link_result* per_frame, int32_t* orders, double* taps_out);
+
 /* FP32 FFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per FFMA) on the current device,
  * the roofline denominator SURVEY 8(d) asks for; <0 on error. */
 double ofdm_b200_measure_fp32_tflops(int32_t iters);

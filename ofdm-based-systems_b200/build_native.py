@@ -49,6 +49,8 @@ def _units():
     units = [("ofdm_b200", os.path.join(CSRC, "ofdm_b200.cu"), [])]
     if os.path.exists(os.path.join(CSRC, "waterfill.cu")):
         units.append(("waterfill", os.path.join(CSRC, "waterfill.cu"), []))
+    if os.path.exists(os.path.join(CSRC, "frames.cu")):
+        units.append(("frames", os.path.join(CSRC, "frames.cu"), []))
     if os.path.exists(os.path.join(CSRC, "link_fast.cu")):
         units.append(("link_fast", os.path.join(CSRC, "link_fast.cu"), []))
     if os.path.exists(os.path.join(CSRC, "link_fast_inst.cu")):

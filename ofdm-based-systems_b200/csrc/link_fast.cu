@@ -8,6 +8,20 @@ namespace ofdm {
 template <int E, int T>
 int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, cudaStream_t stream);
 
+template <int E, int T>
+int launch_frames_shape(int sms, const FastParams& p, cudaStream_t stream);
+
+int launch_fast_frames(int n_subcarriers, int sms, const FastParams& p, cudaStream_t stream) {
+  switch (n_subcarriers) {
+    case 64: return launch_frames_shape<8, 8>(sms, p, stream);
+    case 256: return launch_frames_shape<16, 16>(sms, p, stream);
+    case 1024: return launch_frames_shape<32, 32>(sms, p, stream);
+    case 2048: return launch_frames_shape<32, 64>(sms, p, stream);
+    case 4096: return launch_frames_shape<32, 128>(sms, p, stream);
+    default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", n_subcarriers);
+  }
+}
+
 bool fast_supports_n(int n) { return n == 64 || n == 256 || n == 1024 || n == 2048 || n == 4096; }
 int fast_samples_per_lane(int n) { return n == 64 ? 8 : n == 256 ? 16 : 32; }
 

@@ -28,6 +28,13 @@ namespace ofdm {
 
 constexpr int kFastTaps = 8;
 
+struct FrameHeader {       // per channel realisation (built on the device by frames.cu)
+  float2 taps[kFastTaps];  // unit-energy taps / sqrt(N)
+  float sigma;             // per-component noise standard deviation
+  float mmse_c;            // as FastParams::mmse_c
+  float pad[2];
+};
+
 struct FastParams {
   float2 taps[kFastTaps];   // unit-energy taps / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1), IFFT unscaled)
   const float4* eq_tab;     // {Re A, Im A, G, -}: decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1)
@@ -62,6 +69,13 @@ struct FastParams {
   const unsigned int* field_masks;   // [(E/4) * T]: word j of lane t = ((s_k - 1) << 1) in byte i for k = t + T (4 j + i)
   const float2* level_tab;           // [N]: {g_k, -(2^23 + s_k)} with g_k = 1 / sqrt(2 (M_k - 1) / 3)  (0 when silent);
                                      // the slicer's s_k - 1 is the 4th component of eq_tab
+  // FRAMES instantiation (always with ADAPT): a batch of channel realisations, `frame_syms` OFDM symbols each.
+  // eq_tab / level_tab / field_masks hold one table per frame ([F][N], [F][N], [F][N/4]); a (frame, chunk) unit is
+  // processed by one block, which loads the frame's tables into shared memory when the frame changes.
+  const FrameHeader* frame_hdr;        // [F]
+  unsigned long long* frame_counters;  // [F][10]: 8 counters, power sum (double), power max (double bits)
+  unsigned long long frame_syms;       // OFDM symbols per frame
+  unsigned int n_frames, chunks_per_frame, chunk_syms;
   const void* noise;        // complex64 (noise_f64 = 0) or complex128 (noise_f64 = 1); NULL = noiseless
   int noise_f64;
 };
@@ -153,9 +167,10 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 }
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
-          int NROUNDS = 10, int FIR_UNROLL = 2>
+          bool FRAMES = false, int NROUNDS = 10, int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
   static_assert(!(ADAPT && REPLAY), "recorded streams with per-subcarrier orders run on the general kernel");
+  static_assert(!FRAMES || (ADAPT && !DUMP && !REPLAY), "frame batches: fused mode with per-frame tables");
   using G = FastGeometry<E, T, BLOCK>;
   constexpr int N = G::N, RS = G::RS, WORDS = E / 4, W = G::W;
   constexpr int CALLS = (E + 15) / 16;  // Philox calls for E random bytes
@@ -177,16 +192,25 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 
   // block-resident copies of the twiddle and equaliser tables
   for (int i = threadIdx.x; i < G::TW_F2; i += BLOCK) s_tw[i] = __ldg(&p.tw[i]);
-  for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[i]);
+  if constexpr (!FRAMES) {
+    for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[i]);
+  }
   __syncthreads();
 
-  const unsigned long long n_teams = (unsigned long long)gridDim.x * G::TEAMS;
-  const unsigned long long team_id = (unsigned long long)blockIdx.x * G::TEAMS + team_in_block;
-  const unsigned long long iters = (p.sym_count + n_teams - 1) / n_teams;
   const PhiloxKey key{(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
   const int P = p.prefix_len;
   const float magic = 8388608.0f;  // 2^23
-  const float noise_c2 = -1.3862943611198906f * p.sigma * p.sigma;
+  // symbols of this pass: s = s_lo + it * s_stride + s_first < s_hi, global index sym_base + s.  One pass over the
+  // launch's range, or (FRAMES) one pass per (frame, chunk) unit with the whole block on the same frame.
+  unsigned long long s_lo = 0, s_hi = p.sym_count, sym_base = p.sym_begin;
+  unsigned long long s_stride = (unsigned long long)gridDim.x * G::TEAMS;
+  unsigned long long s_first = (unsigned long long)blockIdx.x * G::TEAMS + team_in_block;
+  float noise_c2 = -1.3862943611198906f * p.sigma * p.sigma;
+  float mmse_c = p.mmse_c;
+  const float2* level_tab = p.level_tab;
+  __shared__ FrameHeader s_hdr;
+  [[maybe_unused]] unsigned long long unit = blockIdx.x;
+  [[maybe_unused]] long long cur_frame = -1;
 
   unsigned long long acc_bit_err = 0, acc_sym_err = 0, acc_syms = 0;
   double acc_pow = 0.0;
@@ -195,14 +219,15 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   // ADAPT: this lane's packed field masks; bits per OFDM symbol carried by its E subcarriers
   unsigned fmask[ADAPT ? WORDS : 1];
   unsigned lane_bits = E * 2 * p.half_bits;
-  if constexpr (ADAPT) {
+  auto load_masks = [&](const unsigned* masks) {
     lane_bits = 0;
 #pragma unroll
     for (int j = 0; j < WORDS; ++j) {
-      fmask[j] = __ldg(&p.field_masks[j * T + t]);
-      lane_bits += 2 * __popc(fmask[j]);
+      fmask[ADAPT ? j : 0] = __ldg(&masks[j * T + t]);
+      lane_bits += 2 * __popc(fmask[ADAPT ? j : 0]);
     }
-  }
+  };
+  if constexpr (ADAPT && !FRAMES) load_masks(p.field_masks);
 
   unsigned next_bits[REPLAY ? WORDS : 1];
   auto replay_prefetch = [&](unsigned long long sn) {
@@ -220,12 +245,68 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
       }
     }
   };
-  replay_prefetch(team_id);
+  replay_prefetch(s_first);
 
+  auto flush_counters = [&](unsigned long long* counters, double* power_sum, unsigned long long* power_max_bits) {
+    // ---- counters: warp shuffle, one atomic per warp
+    auto warp_sum64 = [](unsigned long long x) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+      return x;
+    };
+    const unsigned long long b0 = warp_sum64(acc_bit_err), b2 = warp_sum64(acc_sym_err), b3 = warp_sum64(acc_syms);
+    const unsigned long long bits_total = warp_sum64((acc_syms / E) * lane_bits);
+    const unsigned long long b4 = warp_sum64(t == 0 ? acc_syms / E : 0ull);   // OFDM symbols: one lane per team counts
+    double pw = acc_pow;
+    float mx = acc_max;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      pw += __shfl_down_sync(0xffffffffu, pw, off);
+      mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, off));
+    }
+    if (lane == 0) {
+      if (b0) atomicAdd(&counters[CNT_BIT_ERRORS], b0);
+      if (b3) {
+        atomicAdd(&counters[CNT_BITS], bits_total);
+        atomicAdd(&counters[CNT_SYMBOLS], b3);
+        if (b4) atomicAdd(&counters[CNT_OFDM_SYMBOLS], b4);
+      }
+      if (b2) atomicAdd(&counters[CNT_SYM_ERRORS], b2);
+      if (PAPR) {
+        atomicAdd(power_sum, pw * double(p.tx_scale2));
+        atomicMax(power_max_bits, (unsigned long long)__double_as_longlong(double(mx) * double(p.tx_scale2)));
+      }
+    }
+  };
+
+  do {
+  if constexpr (FRAMES) {
+    if (unit >= (unsigned long long)p.n_frames * p.chunks_per_frame) break;
+    const unsigned long long f = unit / p.chunks_per_frame, c = unit - f * p.chunks_per_frame;
+    if ((long long)f != cur_frame) {
+      // the whole block moves to frame f: its equaliser table and header into shared memory, masks into registers
+      __syncthreads();
+      for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[f * N + i]);
+      if (threadIdx.x < (int)(sizeof(FrameHeader) / sizeof(float)))
+        reinterpret_cast<float*>(&s_hdr)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(&p.frame_hdr[f]) + threadIdx.x);
+      __syncthreads();
+      load_masks(p.field_masks + f * (N / 4));
+      level_tab = p.level_tab + f * N;
+      noise_c2 = -1.3862943611198906f * s_hdr.sigma * s_hdr.sigma;
+      mmse_c = s_hdr.mmse_c;
+      cur_frame = (long long)f;
+    }
+    s_lo = c * p.chunk_syms;
+    s_hi = s_lo + p.chunk_syms < p.frame_syms ? s_lo + p.chunk_syms : p.frame_syms;
+    s_stride = G::TEAMS;
+    s_first = team_in_block;
+    sym_base = p.sym_begin + f * p.frame_syms;
+  }
+  const unsigned long long iters = s_hi > s_lo ? (s_hi - s_lo + s_stride - 1) / s_stride : 0;
   for (unsigned long long it = 0; it < iters; ++it) {
-    const unsigned long long s = it * n_teams + team_id;
-    const bool active = s < p.sym_count;
-    const unsigned long long gs = p.sym_begin + (active ? s : 0ull);
+    const unsigned long long s = s_lo + it * s_stride + s_first;
+    const bool active = s < s_hi;
+    const unsigned long long gs = sym_base + (active ? s : s_lo);
     const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
 
     unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1..4 of each byte
@@ -248,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             if (t + T * j < sym_words) wscr[t + T * j] = __byte_perm(next_bits[j], 0u, 0x0123);
           if (t == 0) wscr[sym_words] = 0u;
           // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
-          replay_prefetch(s + n_teams);
+          replay_prefetch(s + s_stride);
           tsync();
 #pragma unroll
           for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
@@ -291,7 +372,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const unsigned fr = __byte_perm(txr[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
           if constexpr (ADAPT) {
             // per-subcarrier side s_k and power normalisation: (f - (2^23 + s_k)) is the exact integer level
-            const float2 g = __ldg(&p.level_tab[t + T * m]);
+            const float2 g = __ldg(&level_tab[t + T * m]);
             v[m] = make_float2(-(__uint_as_float(fr) + g.y) * g.x, (__uint_as_float(fc) + g.y) * g.x);
           } else {
             const float li = __uint_as_float(fc) + cen;        // I level:  2*col - (s-1)
@@ -329,7 +410,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
             for (int l = 0; l < kFastTaps; ++l) {
               const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
-              const float2 h = p.taps[l];
+              const float2 h = FRAMES ? s_hdr.taps[l] : p.taps[l];
               yr = fmaf(h.x, x.x, yr);
               yr = fmaf(-h.y, x.y, yr);
               yi = fmaf(h.x, x.y, yi);
@@ -485,7 +566,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
           for (int i = 0; i < W; ++i) ss += s_red[i];
         }
-        const float sigma2 = ss * p.mmse_c;
+        const float sigma2 = ss * mmse_c;
         unsigned rxc[WORDS], rxr[WORDS];
 #pragma unroll
         for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
@@ -499,7 +580,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const float inv = fast_rcp(e.z + sigma2);
           if constexpr (DUMP) {
             if (active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
-            const float zu = ADAPT ? 2.f * e.w * __ldg(&p.level_tab[k]).x : p.z_unscale;   // 2 (s_k - 1) / knorm_k
+            const float zu = ADAPT ? 2.f * e.w * __ldg(&level_tab[k]).x : p.z_unscale;   // 2 (s_k - 1) / knorm_k
             if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);
           }
           // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
@@ -546,35 +627,16 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     }
   }
 
-  // ---- counters: warp shuffle, one atomic per warp
-  auto warp_sum64 = [](unsigned long long x) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-    return x;
-  };
-  const unsigned long long b0 = warp_sum64(acc_bit_err), b2 = warp_sum64(acc_sym_err), b3 = warp_sum64(acc_syms);
-  const unsigned long long bits_total = warp_sum64((acc_syms / E) * lane_bits);
-  const unsigned long long b4 = warp_sum64(t == 0 ? acc_syms / E : 0ull);   // OFDM symbols: one lane per team counts
-  double pw = acc_pow;
-  float mx = acc_max;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    pw += __shfl_down_sync(0xffffffffu, pw, off);
-    mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, off));
+  if constexpr (FRAMES) {
+    unsigned long long* fc = p.frame_counters + (unsigned long long)cur_frame * 10;
+    flush_counters(fc, reinterpret_cast<double*>(fc + 8), fc + 9);
+    acc_bit_err = acc_sym_err = acc_syms = 0;
+    acc_pow = 0.0;
+    acc_max = 0.f;
+    unit += gridDim.x;
   }
-  if (lane == 0) {
-    if (b0) atomicAdd(&p.counters[CNT_BIT_ERRORS], b0);
-    if (b3) {
-      atomicAdd(&p.counters[CNT_BITS], bits_total);
-      atomicAdd(&p.counters[CNT_SYMBOLS], b3);
-      if (b4) atomicAdd(&p.counters[CNT_OFDM_SYMBOLS], b4);
-    }
-    if (b2) atomicAdd(&p.counters[CNT_SYM_ERRORS], b2);
-    if (PAPR) {
-      atomicAdd(p.tx_power_sum, pw * double(p.tx_scale2));
-      atomicMax(p.tx_power_max_bits, (unsigned long long)__double_as_longlong(double(mx) * double(p.tx_scale2)));
-    }
-  }
+  } while (FRAMES);
+  if constexpr (!FRAMES) flush_counters(p.counters, p.tx_power_sum, p.tx_power_max_bits);
 }
 
 }  // namespace ofdm

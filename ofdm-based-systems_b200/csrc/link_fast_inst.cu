@@ -10,6 +10,42 @@
 
 namespace ofdm {
 
+template <int E, int T>
+int launch_frames_shape(int sms, const FastParams& p, cudaStream_t stream);
+
+// frame batches (frames.cu): one block per (frame, chunk of symbols) unit, grid-stride over the units
+template <>
+int launch_frames_shape<OFDM_FAST_E, OFDM_FAST_T>(int sms, const FastParams& p0, cudaStream_t stream) {
+  constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T, BLOCK = 512, SYNC = T > 32 ? 0 : 2;
+  using G = FastGeometry<E, T, BLOCK>;
+  auto kern = ofdm_link_fast_kernel<E, T, false, true, false, BLOCK, SYNC, true, true>;
+  static int occ = 0;
+  if (occ == 0) {
+    if (G::SMEM_BYTES > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::BLOCK, G::SMEM_BYTES));
+    if (occ <= 0) occ = 1;
+  }
+  FastParams p = p0;
+  // split a frame into chunks (multiples of the symbols a block holds in flight) until every SM has ~2 units
+  const unsigned long long slots = (unsigned long long)sms * occ, S = p.frame_syms;
+  const unsigned long long max_chunks = (S + G::TEAMS - 1) / G::TEAMS;
+  unsigned long long cpf = (2 * slots + p.n_frames - 1) / p.n_frames;
+  if (cpf < 1) cpf = 1;
+  if (cpf > max_chunks) cpf = max_chunks;
+  unsigned long long chunk = (S + cpf - 1) / cpf;
+  chunk = (chunk + G::TEAMS - 1) / G::TEAMS * G::TEAMS;
+  cpf = (S + chunk - 1) / chunk;
+  p.chunk_syms = (unsigned)chunk;
+  p.chunks_per_frame = (unsigned)cpf;
+  const unsigned long long units = cpf * p.n_frames;
+  const unsigned long long grid = units < slots ? units : slots;
+  kern<<<(unsigned)grid, G::BLOCK, G::SMEM_BYTES, stream>>>(p);
+  count_launch();
+  CUDA_TRY(cudaGetLastError());
+  return OFDM_OK;
+}
+
 template <int E, int T, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2, bool ADAPT = false>
 static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
   using G = FastGeometry<E, T, BLOCK>;

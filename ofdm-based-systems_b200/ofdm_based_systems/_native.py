@@ -46,6 +46,12 @@ class WaterfillDesc(C.Structure):
                 ("capacity_scaling", C.c_double)]
 
 
+class FramesDesc(C.Structure):
+    _fields_ = [("n_subcarriers", C.c_int32), ("prefix_len", C.c_int32), ("equalizer", C.c_int32), ("n_taps", C.c_int32),
+                ("loading", C.c_int32), ("fixed_order", C.c_int32), ("waterfilling", C.c_int32), ("min_order", C.c_int32),
+                ("max_order", C.c_int32), ("device", C.c_int32), ("snr_db", C.c_double), ("gap", C.c_double)]
+
+
 class LinkDump(C.Structure):
     _fields_ = [("y", C.c_void_p), ("z", C.c_void_p), ("rx_labels", C.c_void_p), ("tx_labels", C.c_void_p),
                 ("noise", C.c_void_p)]
@@ -57,7 +63,7 @@ EXPORTS = (
     "ofdm_link_uses_fast_kernel",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
     "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr",
-    "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev",
+    "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev", "ofdm_frames_run",
 )
 
 
@@ -91,6 +97,7 @@ def _load() -> C.CDLL:
     lib.ofdm_link_counters_device_ptr.restype = vp
     lib.ofdm_waterfill_bitload_batched.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     lib.ofdm_waterfill_bitload_batched_dev.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
+    lib.ofdm_frames_run.argtypes = [C.POINTER(FramesDesc), vp, C.c_int64, u64, u64, u32, u64, C.POINTER(LinkResult), vp, vp, vp]
     if lib.ofdm_b200_abi_version() != 1:
         raise NativeLibraryMissing(f"{LIB_PATH}: ABI version {lib.ofdm_b200_abi_version()} != 1, rebuild it")
     return lib
@@ -297,6 +304,35 @@ def compare_allocations_batched(taps: np.ndarray, n_subcarriers: int, snr_db: fl
     cu, cw = uni["capacity"].sum(axis=1), wf["capacity"].sum(axis=1)
     return {"uniform_capacity": cu, "waterfilling_capacity": cw, "capacity_gain": cw - cu,
             "capacity_gain_percent": np.where(cu > 0, 100 * (cw - cu) / np.where(cu > 0, cu, 1), 0.0)}
+
+
+def run_frames(n_subcarriers: int, n_frames: int, symbols_per_frame: int, snr_db: float, *, taps: Optional[np.ndarray] = None,
+               n_taps: int = 8, prefix_len: Optional[int] = None, equalizer: str = "MMSE", order: Optional[int] = None,
+               waterfilling: bool = True, min_order: int = 4, max_order: int = 256, ser: float = 1e-3, seed: int = 0x0FD3,
+               point: int = 0, first_frame: int = 0, device: int = -1, per_frame: bool = True):
+    """A batch of channel realisations in one launch (ofdm_frames_run).  ``taps`` [F, L] complex RAW taps, or None for
+    a fresh Rayleigh draw per frame on the device.  ``order`` = one QAM order on every subcarrier; None = per-frame
+    gap-rule orders (water-filling or uniform power) bounded to [min_order, max_order].
+    Returns dict(total LinkCounters, frames [F] list of LinkCounters, orders [F, N], taps [F, L])."""
+    require_gpu()
+    if taps is not None:
+        taps = np.ascontiguousarray(np.atleast_2d(taps), dtype=np.complex128)
+        if taps.shape[0] != n_frames:
+            raise ValueError("taps must hold one row of raw taps per frame")
+        n_taps = taps.shape[1]
+    n = int(n_subcarriers)
+    desc = FramesDesc(n, int(n_taps - 1 if prefix_len is None else prefix_len), EQUALIZER[equalizer], int(n_taps),
+                      0 if order is not None else 1, int(order or 0), int(bool(waterfilling)), int(min_order), int(max_order),
+                      int(device), float(snr_db), bit_loading_gap(ser, "QAM"))
+    total = LinkResult()
+    frames = (LinkResult * n_frames)() if per_frame else None
+    orders = np.empty((n_frames, n), dtype=np.int32)
+    taps_out = np.empty((n_frames, n_taps), dtype=np.complex128)
+    _check(lib.ofdm_frames_run(C.byref(desc), None if taps is None else taps.ctypes.data, n_frames, symbols_per_frame, seed,
+                               point, first_frame, C.byref(total), frames, orders.ctypes.data, taps_out.ctypes.data))
+    return dict(total=LinkCounters.from_struct(total),
+                frames=[LinkCounters.from_struct(r) for r in frames] if per_frame else None,
+                orders=orders.astype(np.int64), taps=taps_out)
 
 
 def measure_fp32_tflops(iters: int = 4096) -> float:

@@ -1,0 +1,94 @@
+"""Frame batches (ofdm_frames_run): many channel realisations in one launch.  Every frame must reproduce the
+single-link path (ofdm_link_run_fused of a link built from the same taps and orders, same Philox counters), which
+the other GPU tests pin to the reference through the oracle."""
+import numpy as np
+import pytest
+
+import ofdm_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+
+def rayleigh(rng, f, l):
+    """examples/generate_channel_models.py:70-78"""
+    h = (rng.normal(size=(f, l)) + 1j * rng.normal(size=(f, l))) / np.sqrt(2) * np.sqrt(np.exp(-np.arange(l) / 2))
+    return h / np.sqrt(np.sum(np.abs(h) ** 2, axis=1, keepdims=True))
+
+
+def single_link(n, taps_raw, orders, P, eq, snr, S, seed, point, first_symbol):
+    from ofdm_based_systems._native import Link
+    from ofdm_based_systems.simulation.sweep import LinkConfig
+    cfg = LinkConfig(num_subcarriers=n, taps_raw=taps_raw, prefix_length=P, equalizator_type=eq, orders=orders)
+    link = Link(n, cfg.taps_chan, cfg.h_eq, orders, prefix_type="CYCLIC", prefix_len=P, equalizer=eq)
+    res = link.run_fused(snr, cfg.noise_sigma(snr), S, seed=seed, point=point, first_symbol=first_symbol)
+    link.close()
+    return res
+
+
+@pytest.mark.parametrize("n,order,eq,S", [(64, 16, "ZF", 100), (256, 64, "MMSE", 37), (1024, 64, "MMSE", 20), (4096, 256, "MMSE", 9)])
+def test_fixed_order_frames_reproduce_single_links(n, order, eq, S):
+    from ofdm_based_systems._native import run_frames
+    rng = np.random.default_rng(n)
+    F, L, snr = 12, 8, 22.0
+    taps = rayleigh(rng, F, L)
+    out = run_frames(n, F, S, snr, taps=taps, equalizer=eq, order=order, seed=99, point=1, first_frame=5)
+    bps = oc.bits_per_symbol(order)
+    assert out["total"].bits == F * S * n * bps and out["total"].ofdm_symbols == F * S
+    assert np.all(out["orders"] == order)
+    tot_err = 0
+    for f in range(F):
+        ref = single_link(n, taps[f], np.full(n, order), L - 1, eq, snr, S, 99, 1, (5 + f) * S)
+        got = out["frames"][f]
+        assert got.bits == ref.bits and got.symbols == ref.symbols and got.ofdm_symbols == S
+        # same Philox draws; the per-frame tables are built on the device (fp64, other summation order): a decision
+        # within one fp32 ulp of a threshold may differ
+        assert abs(got.bit_errors - ref.bit_errors) <= 2 + 0.01 * ref.bit_errors
+        assert abs(got.tx_power_sum - ref.tx_power_sum) < 1e-5 * ref.tx_power_sum
+        assert abs(got.tx_power_max - ref.tx_power_max) < 1e-5 * ref.tx_power_max
+        tot_err += got.bit_errors
+    assert out["total"].bit_errors == tot_err and tot_err > 0
+
+
+@pytest.mark.parametrize("n,wf", [(64, True), (256, False), (1024, True)])
+def test_adaptive_rayleigh_frames(n, wf):
+    """config #4: fresh Rayleigh realisation per frame drawn on the device, water-filling + gap-rule orders bounded
+    to QPSK .. 256-QAM, one launch."""
+    from ofdm_based_systems._native import run_frames
+    F, S, snr = 40, 32, 18.0
+    out = run_frames(n, F, S, snr, n_taps=8, equalizer="MMSE", waterfilling=wf, min_order=4, max_order=256, seed=7)
+    taps = out["taps"]
+    np.testing.assert_allclose(np.sum(np.abs(taps) ** 2, axis=1), 1.0, rtol=1e-12)
+    # exponential power delay profile of the draw (before the per-frame normalisation it is exp(-l/2))
+    big = run_frames(64, 4000, 1, snr, n_taps=8, order=4, seed=3)["taps"]
+    prof = np.mean(np.abs(big) ** 2, axis=0)
+    assert np.all(np.abs(prof / prof[0] - np.exp(-np.arange(8) / 2)) < 0.12)
+    mism = 0
+    for f in range(0, F, 3):
+        orders, _, _ = oc.adaptive_setup(n, taps[f], snr, 1e-3, oc.QAM, waterfill=wf)
+        bounded = np.where(orders > 256, 256, np.where(orders < 4, 0, orders))
+        mism += int(np.sum(out["orders"][f] != bounded))
+        ref = single_link(n, taps[f], out["orders"][f], 7, "MMSE", snr, S, 7, 0, f * S)
+        got = out["frames"][f]
+        assert got.bits == ref.bits == S * sum(oc.bits_per_symbol(int(o)) for o in out["orders"][f] if o > 1)
+        assert abs(got.bit_errors - ref.bit_errors) <= 2 + 0.01 * ref.bit_errors
+    assert mism <= 2
+
+
+def test_frames_shard_like_symbols():
+    from ofdm_based_systems._native import run_frames
+    kw = dict(n_taps=6, equalizer="MMSE", order=16, seed=1234, point=2)
+    whole = run_frames(256, 30, 50, 15.0, **kw)
+    a = run_frames(256, 11, 50, 15.0, first_frame=0, **kw)
+    b = run_frames(256, 19, 50, 15.0, first_frame=11, **kw)
+    np.testing.assert_array_equal(whole["taps"], np.concatenate([a["taps"], b["taps"]]))
+    assert whole["total"].bit_errors == a["total"].bit_errors + b["total"].bit_errors > 0
+    assert whole["total"].bits == a["total"].bits + b["total"].bits
+    assert [r.bit_errors for r in whole["frames"]] == [r.bit_errors for r in a["frames"] + b["frames"]]
+    # many symbols per frame, few frames: the frame is split into chunks over the SMs, same counters
+    few = run_frames(1024, 3, 4000, 20.0, n_taps=8, order=64, seed=5)
+    again = run_frames(1024, 1, 4000, 20.0, n_taps=8, order=64, seed=5, first_frame=1)
+    assert few["frames"][1].bit_errors == again["frames"][0].bit_errors > 0
+    with pytest.raises(ValueError):
+        run_frames(128, 2, 10, 20.0, order=16)
+    with pytest.raises(ValueError):
+        run_frames(256, 2, 10, 20.0, max_order=1024)
