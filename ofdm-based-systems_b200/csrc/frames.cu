@@ -138,10 +138,26 @@ __global__ void __launch_bounds__(kFtThreads) frame_tables_kernel(const FrameTab
   }
 }
 
+// scratch arena kept across calls (cudaMalloc / cudaFree of a few hundred MB cost more than the kernels); one per
+// host thread, regrown on demand, released when the thread ends
 struct DeviceArena {
   unsigned char* base = nullptr;
-  ~DeviceArena() { cudaFree(base); }
+  size_t bytes = 0;
+  int device = -1;
+  int reserve(size_t need, int dev) {
+    if (base && device == dev && bytes >= need) return OFDM_OK;
+    if (base) cudaFree(base);
+    base = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&base, need);
+    if (e != cudaSuccess) return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of frame tables) failed: %s", need, cudaGetErrorString(e));
+    bytes = need;
+    device = dev;
+    return OFDM_OK;
+  }
+  ~DeviceArena() { if (base) cudaFree(base); }
 };
+thread_local DeviceArena g_arena;
 
 }  // namespace
 }  // namespace ofdm
@@ -185,12 +201,13 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
                o_heq = up(o_lvl + F * 8), o_eq = up(o_heq + F * N * 16), o_level = up(o_eq + F * N * 16),
                o_mask = up(o_level + F * N * 8), o_hdr = up(o_mask + F * N), o_cnt = up(o_hdr + F * sizeof(FrameHeader)),
                o_used = up(o_cnt + F * 80), bytes = o_used + (orders_out ? F * N * 4 : 0);
-  DeviceArena arena;
+  const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
+  const size_t tw_count = size_t(E - 1) * E + (Wd > 1 ? N / Wd : 0), o_tw = up(bytes);
   {
-    cudaError_t e = cudaMalloc(&arena.base, bytes);
-    if (e != cudaSuccess) return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes for %zu frames) failed: %s", bytes, F, cudaGetErrorString(e));
+    const int rc_arena = g_arena.reserve(o_tw + tw_count * sizeof(float2), dev);
+    if (rc_arena) return rc_arena;
   }
-  unsigned char* a = arena.base;
+  unsigned char* a = g_arena.base;
   cudaStream_t stream = nullptr;
   double2* d_taps = reinterpret_cast<double2*>(a + o_taps);
   if (taps) {
@@ -232,7 +249,7 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
   tp.orders_used = orders_out ? reinterpret_cast<int*>(a + o_used) : nullptr;
   tp.n = N;
   tp.n_taps = L;
-  tp.E = fast_samples_per_lane(N);
+  tp.E = E;
   tp.equalizer = d->equalizer;
   tp.fixed_order = d->loading == 0 ? d->fixed_order : 0;
   tp.snr_lin = std::pow(10.0, d->snr_db / 10.0);
@@ -241,7 +258,6 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
   CUDA_TRY(cudaGetLastError());
 
   // pass-2 / pass-3 twiddles of the fast transform (same table as ofdm_link_create builds)
-  const int E = tp.E, T = N / E, Wd = T / E;
   std::vector<float2> tw;
   for (int r = 1; r < E; ++r)
     for (int k = 0; k < E; ++k) {
@@ -253,9 +269,7 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
       const double ang = -2.0 * M_PI * double(j) / double(N);
       tw.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
     }
-  float2* d_tw = nullptr;
-  CUDA_TRY(cudaMalloc(&d_tw, tw.size() * sizeof(float2)));
-  struct FreeTw { float2* p; ~FreeTw() { cudaFree(p); } } free_tw{d_tw};
+  float2* d_tw = reinterpret_cast<float2*>(a + o_tw);
   CUDA_TRY(cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
 
   FastParams fp;

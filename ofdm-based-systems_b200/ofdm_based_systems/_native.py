@@ -309,11 +309,13 @@ def compare_allocations_batched(taps: np.ndarray, n_subcarriers: int, snr_db: fl
 def run_frames(n_subcarriers: int, n_frames: int, symbols_per_frame: int, snr_db: float, *, taps: Optional[np.ndarray] = None,
                n_taps: int = 8, prefix_len: Optional[int] = None, equalizer: str = "MMSE", order: Optional[int] = None,
                waterfilling: bool = True, min_order: int = 4, max_order: int = 256, ser: float = 1e-3, seed: int = 0x0FD3,
-               point: int = 0, first_frame: int = 0, device: int = -1, per_frame: bool = True):
+               point: int = 0, first_frame: int = 0, device: int = -1, per_frame: bool = True,
+               want_orders: bool = True, want_taps: bool = True):
     """A batch of channel realisations in one launch (ofdm_frames_run).  ``taps`` [F, L] complex RAW taps, or None for
     a fresh Rayleigh draw per frame on the device.  ``order`` = one QAM order on every subcarrier; None = per-frame
     gap-rule orders (water-filling or uniform power) bounded to [min_order, max_order].
-    Returns dict(total LinkCounters, frames [F] list of LinkCounters, orders [F, N], taps [F, L])."""
+    Returns dict(total LinkCounters, frames [F] list of LinkCounters, orders [F, N], taps [F, L]); the last three are
+    None when not requested (they are the only per-frame device -> host traffic)."""
     require_gpu()
     if taps is not None:
         taps = np.ascontiguousarray(np.atleast_2d(taps), dtype=np.complex128)
@@ -326,13 +328,14 @@ def run_frames(n_subcarriers: int, n_frames: int, symbols_per_frame: int, snr_db
                       int(device), float(snr_db), bit_loading_gap(ser, "QAM"))
     total = LinkResult()
     frames = (LinkResult * n_frames)() if per_frame else None
-    orders = np.empty((n_frames, n), dtype=np.int32)
-    taps_out = np.empty((n_frames, n_taps), dtype=np.complex128)
+    orders = np.empty((n_frames, n), dtype=np.int32) if want_orders else None
+    taps_out = np.empty((n_frames, n_taps), dtype=np.complex128) if want_taps else None
     _check(lib.ofdm_frames_run(C.byref(desc), None if taps is None else taps.ctypes.data, n_frames, symbols_per_frame, seed,
-                               point, first_frame, C.byref(total), frames, orders.ctypes.data, taps_out.ctypes.data))
+                               point, first_frame, C.byref(total), frames, None if orders is None else orders.ctypes.data,
+                               None if taps_out is None else taps_out.ctypes.data))
     return dict(total=LinkCounters.from_struct(total),
                 frames=[LinkCounters.from_struct(r) for r in frames] if per_frame else None,
-                orders=orders.astype(np.int64), taps=taps_out)
+                orders=None if orders is None else orders.astype(np.int64), taps=taps_out)
 
 
 def measure_fp32_tflops(iters: int = 4096) -> float:
