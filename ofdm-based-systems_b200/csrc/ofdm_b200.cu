@@ -3,6 +3,7 @@
 #include "../../include/ofdm_b200.h"
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <complex>
 #include <cstdarg>
@@ -21,6 +22,40 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+
+// Link arenas are a few tens of KB and links are created per channel realisation / per sweep: recycle them instead
+// of paying cudaMalloc + cudaFree (which synchronises the device) every time.  Small bounded cache, any thread.
+struct ArenaCache {
+  struct Entry { unsigned char* ptr; size_t bytes; int device; };
+  std::mutex mu;
+  std::vector<Entry> free_list;
+  unsigned char* acquire(size_t bytes, int device) {
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      for (size_t i = 0; i < free_list.size(); ++i)
+        if (free_list[i].device == device && free_list[i].bytes >= bytes && free_list[i].bytes <= 2 * bytes + 4096) {
+          unsigned char* p = free_list[i].ptr;
+          free_list.erase(free_list.begin() + i);
+          return p;
+        }
+    }
+    unsigned char* p = nullptr;
+    return cudaMalloc(&p, bytes) == cudaSuccess ? p : nullptr;
+  }
+  void release(unsigned char* ptr, size_t bytes, int device) {
+    if (!ptr) return;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (free_list.size() < 16) {
+        free_list.push_back({ptr, bytes, device});
+        return;
+      }
+    }
+    cudaFree(ptr);
+  }
+  ~ArenaCache() { for (auto& e : free_list) cudaFree(e.ptr); }
+};
+ArenaCache g_arenas;
 
 }  // namespace
 
@@ -400,8 +435,8 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   if (!tw_fast_host.empty()) std::memcpy(stage.data() + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
   if (!level_host.empty()) std::memcpy(stage.data() + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
   if (!mask_host.empty()) std::memcpy(stage.data() + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
-  unsigned char* arena = nullptr;
-  CUDA_TRY(cudaMalloc(&arena, total));
+  unsigned char* arena = g_arenas.acquire(total, dev);
+  if (!arena) { delete L; cudaGetLastError(); return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of link tables) failed", total); }
   L->arena = arena;
   CUDA_TRY(cudaMemcpy(arena, stage.data(), total, cudaMemcpyHostToDevice));
   L->d_cnt = reinterpret_cast<CounterBlock*>(arena);
@@ -420,7 +455,9 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
 void ofdm_link_destroy(ofdm_link* L) {
   if (!L) return;
   DeviceGuard guard(L->device);
-  cudaFree(L->arena);
+  // the cached arena may be handed to the next link at once: everything this link queued on the device must be done
+  cudaDeviceSynchronize();
+  g_arenas.release(L->arena, L->table_bytes, L->device);
   delete L;
 }
 

@@ -176,4 +176,64 @@ class LinkSweep:
               weak_scaling: bool = False) -> List[dict]:
         """``n_symbols`` is the global OFDM-symbol count per point (the per-rank count with
         ``weak_scaling``); the symbol range is sharded over the ranks of the process group."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            # one GPU: the plain synchronous C-ABI call per point (reset, launch, counters D2H), no torch in the loop
+            spo = self.cfg.num_subcarriers + self.cfg.prefix_length
+            out = []
+            for i, snr in enumerate(snr_dbs):
+                r = self.link.run_fused(float(snr), self.cfg.noise_sigma(float(snr)), n_symbols, seed=seed, point=i)
+                mean_p = r.tx_power_sum / max(r.ofdm_symbols * spo, 1)
+                out.append(dict(snr_db=float(snr), bit_errors=r.bit_errors, total_bits=r.bits, symbol_errors=r.symbol_errors,
+                                num_constellation_symbols=r.symbols, num_ofdm_symbols=r.ofdm_symbols,
+                                bit_error_rate=r.bit_errors / r.bits if r.bits else 0.0,
+                                symbol_error_rate=r.symbol_errors / r.symbols if r.symbols else 0.0,
+                                papr_db=float(10 * np.log10(r.tx_power_max / mean_p)) if mean_p > 0 else float("inf")))
+            return out
         return self.finalize(snr_dbs, self.enqueue(snr_dbs, n_symbols, seed=seed, group=group, weak_scaling=weak_scaling))
+
+
+class FrameSweep:
+    """BER-vs-SNR sweep over a batch of channel realisations ("fresh channel per frame", BASELINE configs #2 / #4):
+    every SNR point is one ``ofdm_frames_run`` call over this rank's contiguous share of the frame range, and ONE
+    all-reduce combines the per-rank totals of all points.  Frame f draws its taps and its OFDM symbols from Philox
+    counters derived from the global frame index, so the union is the same for 1, 2, 4 or 8 GPUs.
+
+    ``frame_kwargs`` are those of ``_native.run_frames`` (n_taps, equalizer, order or waterfilling / min_order /
+    max_order / ser, taps, prefix_len)."""
+
+    def __init__(self, num_subcarriers: int, run_frames=None, **frame_kwargs):
+        self.num_subcarriers = int(num_subcarriers)
+        self.frame_kwargs = frame_kwargs
+        self._run = run_frames if run_frames is not None else _native.run_frames
+
+    def sweep(self, snr_dbs: Sequence[float], n_frames: int, symbols_per_frame: int, *, seed: int = 0x0FD3, group=None,
+              device=None) -> List[dict]:
+        import struct
+        import torch
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank(group) if distributed else 0
+        world = dist.get_world_size(group) if distributed else 1
+        first, count = LinkSweep.shard(n_frames, rank, world)
+        kw = dict(self.frame_kwargs)
+        taps = kw.pop("taps", None)
+        if taps is not None:
+            taps = np.atleast_2d(taps)[first:first + count]
+        rows = torch.zeros((len(snr_dbs), N_WORDS), dtype=torch.int64)
+        bits_of = lambda x: struct.unpack("<q", struct.pack("<d", float(x)))[0]
+        for i, snr in enumerate(snr_dbs):
+            if count == 0:
+                continue
+            r = self._run(self.num_subcarriers, count, symbols_per_frame, float(snr), taps=taps, seed=seed, point=i,
+                          first_frame=first, per_frame=False, want_orders=False, want_taps=False, **kw)["total"]
+            rows[i, :5] = torch.tensor([r.bit_errors, r.bits, r.symbol_errors, r.symbols, r.ofdm_symbols], dtype=torch.int64)
+            rows[i, 8], rows[i, 9] = bits_of(r.tx_power_sum), bits_of(r.tx_power_max)
+        if device is None and distributed and dist.get_backend(group) == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device is not None:
+            rows = rows.to(device)
+        payload = combine_counters(rows, rank, world, group if distributed else None)
+        n_taps = int(kw.get("n_taps", 8)) if taps is None else int(taps.shape[1])
+        prefix = kw.get("prefix_len")
+        return decode_counters(snr_dbs, payload, self.num_subcarriers + (n_taps - 1 if prefix is None else int(prefix)))

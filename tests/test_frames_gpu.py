@@ -92,3 +92,16 @@ def test_frames_shard_like_symbols():
         run_frames(128, 2, 10, 20.0, order=16)
     with pytest.raises(ValueError):
         run_frames(256, 2, 10, 20.0, max_order=1024)
+
+
+def test_frame_sweep_single_rank_matches_direct_calls():
+    from ofdm_based_systems._native import run_frames
+    from ofdm_based_systems.simulation.sweep import FrameSweep
+    res = FrameSweep(256, n_taps=8, equalizer="MMSE", waterfilling=True, min_order=4, max_order=256).sweep(
+        [10.0, 20.0], 24, 40, seed=21)
+    for i, snr in enumerate((10.0, 20.0)):
+        d = run_frames(256, 24, 40, snr, n_taps=8, equalizer="MMSE", waterfilling=True, min_order=4, max_order=256,
+                       seed=21, point=i)["total"]
+        assert res[i]["bit_errors"] == d.bit_errors and res[i]["total_bits"] == d.bits
+        assert abs(res[i]["papr_db"] - d.papr_db) < 1e-9
+    assert res[0]["bit_error_rate"] > 0 and res[1]["total_bits"] > res[0]["total_bits"]   # more bits loaded at 20 dB

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ofdm_based_systems.simulation.sweep import LinkSweep, combine_counters, decode_counters
+from ofdm_based_systems.simulation.sweep import FrameSweep, LinkSweep, combine_counters, decode_counters
 
 
 def _free_port():
@@ -76,3 +76,40 @@ def test_shards_partition_the_symbol_range():
             for (f0, c0), (f1, _) in zip(spans, spans[1:]):
                 assert f0 + c0 == f1
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def _fake_run_frames(n, count, sym_per_frame, snr, *, taps=None, seed=0, point=0, first_frame=0, **kw):
+    """Deterministic stand-in for _native.run_frames: per-frame counters that depend only on the GLOBAL frame index."""
+    from ofdm_based_systems._native import LinkCounters
+    frames = np.arange(first_frame, first_frame + count)
+    errs = int(np.sum((frames * 11 + point * 3 + seed) % 17))
+    if taps is not None:
+        assert taps.shape[0] == count
+        errs += int(np.sum(np.round(np.abs(taps[:, 0]) * 100)))
+    return dict(total=LinkCounters(errs, count * sym_per_frame * n * 4, errs // 3, count * sym_per_frame * n,
+                                   count * sym_per_frame, count * sym_per_frame * (n + 7),
+                                   float(count * sym_per_frame * (n + 7)) * 0.999, 4.0 + float(np.max(frames % 5)) if count else 0.0))
+
+
+def _frame_worker(rank, world, port, n_frames, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    taps = np.linspace(0.1, 1.0, n_frames)[:, None] * np.ones((1, 8))
+    res = FrameSweep(64, run_frames=_fake_run_frames, n_taps=8, order=16, taps=taps).sweep([10.0, 20.0], n_frames, 50, seed=5)
+    np.save(os.path.join(out_dir, f"f{rank}.npy"),
+            np.array([[r["bit_errors"], r["total_bits"], r["num_ofdm_symbols"], r["papr_db"]] for r in res]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [9, 1])
+def test_frame_sweep_shards_frames_across_ranks(tmp_path, n_frames):
+    world = 2
+    mp.spawn(_frame_worker, args=(world, _free_port(), n_frames, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "f0.npy"), np.load(tmp_path / "f1.npy")
+    np.testing.assert_array_equal(r0, r1)
+    taps = np.linspace(0.1, 1.0, n_frames)[:, None] * np.ones((1, 8))
+    single = FrameSweep(64, run_frames=_fake_run_frames, n_taps=8, order=16, taps=taps).sweep([10.0, 20.0], n_frames, 50, seed=5)
+    for p in range(2):
+        assert r0[p, 0] == single[p]["bit_errors"] and r0[p, 1] == single[p]["total_bits"] == n_frames * 50 * 64 * 4
+        assert r0[p, 2] == n_frames * 50
+        assert abs(r0[p, 3] - single[p]["papr_db"]) < 1e-9
