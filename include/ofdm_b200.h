@@ -76,6 +76,13 @@ int ofdm_b200_device_count(void);
  */
 int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const double* h_eq,
                      const int32_t* orders, const double* amp, ofdm_link** out);
+/* Same with APPLIED power loading, which Simulation.run() never does (simulation/models.py:508) but the reference's
+ * experiments do (examples/overview.py:142, examples/waterfilling_noise_bump_experiment.py:148, 165-169):
+ *   amp     : N tx amplitudes sqrt(P_k) multiplying the unit-power constellation points
+ *   rx_gain : N receiver gains multiplying the equalised subcarriers before the demapper (1 / sqrt(P_k), 1 where
+ *             P_k ~ 0), or NULL = no compensation */
+int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan, const double* h_eq,
+                            const int32_t* orders, const double* amp, const double* rx_gain, ofdm_link** out);
 void ofdm_link_destroy(ofdm_link* link);
 int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* link);
 /* 1 when this link shape runs on the register-resident fast kernel (csrc/link_fast.cuh), 0 when it runs on

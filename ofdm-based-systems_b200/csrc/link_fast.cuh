@@ -580,7 +580,8 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const float inv = fast_rcp(e.z + sigma2);
           if constexpr (DUMP) {
             if (active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
-            const float zu = ADAPT ? 2.f * e.w * __ldg(&level_tab[k]).x : p.z_unscale;   // 2 (s_k - 1) / knorm_k
+            // 2 (s_k - 1) / knorm_k with knorm_k^2 = 2 (M_k - 1) / 3, M_k = (top + 1)^2
+            const float zu = ADAPT ? 2.f * e.w * rsqrtf(fmaxf((e.w * e.w + 2.f * e.w) * (2.f / 3.f), 1e-30f)) : p.z_unscale;
             if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);
           }
           // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index

@@ -412,6 +412,10 @@ __global__ void __launch_bounds__(Geometry<N, E>::BLOCK) ofdm_link_kernel(const 
         r[m] = cmul(r[m], make_float2(e.x, e.y));
       }
     }
+    if (p.rx_gain) {  // receiver compensation of the applied power loading (examples/waterfilling_noise_bump_experiment.py:165-169)
+#pragma unroll
+      for (int m = 0; m < E; ++m) r[m] = cscale(r[m], __ldg(&p.sc_tab[t + T * m]).w);
+    }
     if (p.modulator == MOD_SC) {  // SC-OFDM: back to the time domain (modulation/models.py:89)
       team_fft<N, E, +1>(r, buf, p.tw, team);
 #pragma unroll

@@ -20,8 +20,9 @@ struct LinkParams {
   int noise_src;  // SRC_NONE | SRC_PHILOX | SRC_REPLAY_F32 | SRC_REPLAY_F64
   int isi;        // 1: the FIR reaches into the previous OFDM symbol -> chained processing with a halo
   int limit_bits; // 1: bit positions >= compare_limit are not compared (ragged tail of a replayed stream)
+  int rx_gain;    // 1: the equalised subcarrier k is multiplied by sc_tab[k].w before the demapper
   float2 taps[kMaxTaps];  // unit-energy channel taps (channel/models.py:14-16)
-  const float4* sc_tab;   // per subcarrier {amp, slicer scale k, bits(bps | bit_offset << 8), -}
+  const float4* sc_tab;   // per subcarrier {amp, slicer scale k, bits(bps | bit_offset << 8), receiver gain}
   const float4* eq_tab;   // per subcarrier ZF {Re 1/H, Im 1/H, -, -} | MMSE {Re H, Im H, |H|^2, -}
   const float2* tw;       // inter-pass twiddles (forward sign), see LinkPlan::build_twiddles
   float sigma;            // fused mode: per-component noise standard deviation

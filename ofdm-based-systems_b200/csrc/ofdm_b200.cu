@@ -123,6 +123,7 @@ void fill_params(const ofdm_link* L, LinkParams& p, double snr_db) {
   p.scheme = L->d.scheme;
   p.n_taps = L->d.n_taps;
   p.isi = L->isi;
+  p.rx_gain = L->rx_gain;
   std::memcpy(p.taps, L->taps, sizeof(p.taps));
   p.sc_tab = L->d_sc;
   p.eq_tab = L->d_eq;
@@ -290,6 +291,11 @@ int ofdm_b200_device_count(void) {
 
 int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const double* h_eq, const int32_t* orders,
                      const double* amp, ofdm_link** out) {
+  return ofdm_link_create_loaded(desc, taps_chan, h_eq, orders, amp, nullptr, out);
+}
+
+int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan, const double* h_eq, const int32_t* orders,
+                            const double* amp, const double* rx_gain, ofdm_link** out) {
   if (!desc || !taps_chan || !h_eq || !orders || !out) return fail(OFDM_EINVAL, "null argument");
   const int N = desc->n_subcarriers, Lt = desc->n_taps, P = desc->prefix_len;
   if (N < 8 || N > 8192 || (N & (N - 1))) return fail(OFDM_EUNSUPPORTED, "n_subcarriers=%d: need a power of two in 8..8192", N);
@@ -310,6 +316,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
   L->device = dev;
   // consecutive OFDM symbols interact when the prefix is shorter than the channel memory
   L->isi = (Lt - 1 > P) ? 1 : 0;
+  L->rx_gain = rx_gain != nullptr;
   for (int l = 0; l < kMaxTaps; ++l)
     L->taps[l] = l < Lt ? make_float2((float)taps_chan[2 * l], (float)taps_chan[2 * l + 1]) : make_float2(0.f, 0.f);
 
@@ -328,7 +335,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
     const unsigned info = (unsigned)bps | ((unsigned)bit_off << 8);
     float info_f;
     std::memcpy(&info_f, &info, 4);
-    sc[k] = make_float4((float)(a / knorm), (float)knorm, info_f, 0.f);
+    sc[k] = make_float4((float)(a / knorm), (float)knorm, info_f, rx_gain ? (float)rx_gain[k] : 1.f);
     bit_off += bps;
     const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
     sum_h2 += std::norm(H);
@@ -357,10 +364,10 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
       loadable = loadable && (M == 0 || M == 1 || M == 4 || M == 16 || M == 64 || M == 256);
     }
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
-    const bool shape_ok = !amp && desc->scheme == OFDM_SCHEME_QAM && desc->modulator == OFDM_MOD_OFDM &&
+    const bool shape_ok = desc->scheme == OFDM_SCHEME_QAM && desc->modulator == OFDM_MOD_OFDM &&
                           desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 && Lt <= kFastTaps && fast_supports_n(N) &&
                           P < N && !(force && force[0] == '1');
-    L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4) ? 1 : 2;
+    L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
     if (L->fast) {
       const double sqn = std::sqrt((double)N);
       L->fixed_order = L->fast == 1 ? orders[0] : 0;
@@ -387,7 +394,8 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
         if (side == 1) {
           eqf[k] = make_float4(0.f, 0.f, 1.f, 0.f);   // silent subcarrier: decision index 0, no errors counted
         } else {
-          const double dec = knorm_k / (2.0 * sqn * (side - 1));
+          // applied power loading: tx amplitude in the level table, receiver gain in the decision-domain table
+          const double dec = knorm_k / (2.0 * sqn * (side - 1)) * (rx_gain ? rx_gain[k] : 1.0);
           if (desc->equalizer == OFDM_EQ_NONE) {
             eqf[k] = make_float4((float)dec, 0.f, 1.f, top);
           } else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) {
@@ -395,7 +403,7 @@ int ofdm_link_create(const ofdm_link_desc* desc, const double* taps_chan, const 
           } else {
             eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), top);
           }
-          level_host[k] = make_float2((float)(1.0 / knorm_k), -(8388608.0f + float(side)));
+          level_host[k] = make_float2((float)((amp ? amp[k] : 1.0) / knorm_k), -(8388608.0f + float(side)));
           const int t = k % T, m = k / T;
           mask_host[size_t(m / 4) * T + t] |= (unsigned)((side - 1) << 1) << (8 * (m % 4));
         }

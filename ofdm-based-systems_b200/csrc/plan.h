@@ -36,6 +36,7 @@ struct ofdm_link {
   int E = 0, T = 0, block = 0, teams = 0;
   int bits_per_ofdm = 0;
   int isi = 0;
+  int rx_gain = 0;              // 1: a receiver gain per subcarrier was given (applied power loading)
   double mean_h2 = 0.0;
   float2 taps[ofdm::kMaxTaps];
   float4* d_sc = nullptr;

@@ -59,7 +59,7 @@ class LinkDump(C.Structure):
 
 EXPORTS = (
     "ofdm_b200_last_error", "ofdm_b200_abi_version", "ofdm_b200_device_count", "ofdm_b200_launch_count",
-    "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
+    "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_create_loaded", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
     "ofdm_link_uses_fast_kernel",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
     "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr",
@@ -81,6 +81,7 @@ def _load() -> C.CDLL:
     lib.ofdm_b200_measure_fp32_tflops.restype = dbl
     lib.ofdm_b200_measure_fp32_tflops.argtypes = [i32]
     lib.ofdm_link_create.argtypes = [C.POINTER(LinkDesc), vp, vp, vp, vp, C.POINTER(vp)]
+    lib.ofdm_link_create_loaded.argtypes = [C.POINTER(LinkDesc), vp, vp, vp, vp, vp, C.POINTER(vp)]
     lib.ofdm_link_destroy.argtypes = [vp]
     lib.ofdm_link_destroy.restype = None
     lib.ofdm_link_bits_per_ofdm_symbol.argtypes = [vp]
@@ -161,7 +162,8 @@ class Link:
 
     def __init__(self, n_subcarriers: int, taps_chan: np.ndarray, h_eq: np.ndarray, orders: np.ndarray, *,
                  prefix_type: str = "CYCLIC", prefix_len: int = 0, modulator: str = "OFDM", equalizer: str = "MMSE",
-                 scheme: str = "QAM", amp: Optional[np.ndarray] = None, device: int = -1):
+                 scheme: str = "QAM", amp: Optional[np.ndarray] = None, rx_gain: Optional[np.ndarray] = None,
+                 device: int = -1):
         require_gpu()
         taps = np.ascontiguousarray(taps_chan, dtype=np.complex128)
         heq = np.ascontiguousarray(h_eq, dtype=np.complex128)
@@ -169,12 +171,17 @@ class Link:
         if heq.shape != (n_subcarriers,) or ords.shape != (n_subcarriers,):
             raise ValueError("h_eq and orders must have one entry per subcarrier")
         a = None if amp is None else np.ascontiguousarray(amp, dtype=np.float64)
+        g = None if rx_gain is None else np.ascontiguousarray(rx_gain, dtype=np.float64)
+        for arr in (a, g):
+            if arr is not None and arr.shape != (n_subcarriers,):
+                raise ValueError("amp and rx_gain must have one entry per subcarrier")
         self.n_subcarriers, self.prefix_len = int(n_subcarriers), int(prefix_len)
         self.desc = LinkDesc(n_subcarriers, PREFIX[prefix_type], prefix_len, MODULATOR[modulator], EQUALIZER[equalizer],
                              SCHEME[scheme], taps.shape[0], device)
         self._h = C.c_void_p()
-        _check(lib.ofdm_link_create(C.byref(self.desc), taps.ctypes.data, heq.ctypes.data, ords.ctypes.data,
-                                    None if a is None else a.ctypes.data, C.byref(self._h)))
+        _check(lib.ofdm_link_create_loaded(C.byref(self.desc), taps.ctypes.data, heq.ctypes.data, ords.ctypes.data,
+                                           None if a is None else a.ctypes.data, None if g is None else g.ctypes.data,
+                                           C.byref(self._h)))
         self.bits_per_ofdm_symbol = int(lib.ofdm_link_bits_per_ofdm_symbol(self._h))
         self.table_bytes = int(lib.ofdm_link_table_bytes(self._h))
         self.uses_fast_kernel = bool(lib.ofdm_link_uses_fast_kernel(self._h))

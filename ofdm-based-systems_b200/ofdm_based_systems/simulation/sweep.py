@@ -31,6 +31,7 @@ class LinkConfig:
     awgn: bool = True
     orders: Optional[np.ndarray] = None      # adaptive mode: per-subcarrier orders
     amp: Optional[np.ndarray] = None         # optional per-subcarrier tx amplitude (sqrt of allocated power)
+    rx_gain: Optional[np.ndarray] = None     # optional receiver compensation per subcarrier (1 / amp)
     taps_chan: np.ndarray = field(init=False)
     h_eq: np.ndarray = field(init=False)
 
@@ -122,7 +123,8 @@ class LinkSweep:
         self.link = _native.Link(cfg.num_subcarriers, cfg.taps_chan, cfg.h_eq, cfg.orders,
                                  prefix_type=cfg.prefix_scheme, prefix_len=cfg.prefix_length,
                                  modulator=cfg.modulator_type, equalizer=cfg.equalizator_type,
-                                 scheme=cfg.constellation_scheme, amp=cfg.amp, device=-1 if device is None else device)
+                                 scheme=cfg.constellation_scheme, amp=cfg.amp, rx_gain=cfg.rx_gain,
+                                 device=-1 if device is None else device)
         self.device = device
 
     def close(self):

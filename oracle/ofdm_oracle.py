@@ -419,6 +419,11 @@ class LinkSetup:
     awgn: bool = True
     orders: Optional[np.ndarray] = None   # adaptive mode: per-subcarrier orders (len n_sc)
     prefix_len_override: Optional[int] = None  # component-pipeline callers pick P directly
+    # applied power loading, which Simulation.run() never does (simulation/models.py:508) but the reference's
+    # experiments do: tx amplitudes sqrt(P_k) (examples/overview.py:142, examples/waterfilling_noise_bump_experiment.py:148)
+    # and the receiver's compensation 1/sqrt(P_k) on the equalised subcarriers (waterfilling_noise_bump_experiment.py:165-169)
+    amp: Optional[np.ndarray] = None
+    rx_gain: Optional[np.ndarray] = None
     taps_chan: np.ndarray = field(init=False)
     H_eq: np.ndarray = field(init=False)
     prefix_len: int = field(init=False)
@@ -474,6 +479,8 @@ def run_link(setup: LinkSetup, tx_bytes: bytes, total_bits: int, noise: Optional
     if symbols.size % n != 0:
         raise ValueError("Length of data must be divisible by number of streams.")  # serial_parallel/models.py:13
     parallel = symbols.reshape(-1, n)                                                 # :471
+    if setup.amp is not None:
+        parallel = parallel * np.asarray(setup.amp, dtype=np.float64)[None, :]        # noise_bump_experiment.py:148
     tx = modulate(parallel, p, setup.prefix_type, setup.modulator)                    # :514
     papr = papr_db(tx)                                                                # :519-524
     serial = tx.reshape(-1)                                                           # :529
@@ -484,6 +491,10 @@ def run_link(setup: LinkSetup, tx_bytes: bytes, total_bits: int, noise: Optional
     rx_par = rx.reshape(-1, n + p)                                                    # :546-548
     out, Y, Zf = demodulate(rx_par, n, p, setup.prefix_type, setup.eq, setup.H_eq, setup.snr_db,
                             setup.modulator, return_freq=True)                        # :554
+    if setup.rx_gain is not None:
+        if setup.modulator != MOD_OFDM:
+            raise ValueError("receiver power compensation is per subcarrier: OFDM modulator only")
+        out = out * np.asarray(setup.rx_gain, dtype=np.float64)[None, :]              # noise_bump_experiment.py:165-169
     z = out.reshape(-1)
     if setup.adaptive:
         rx_bytes, rx_labels = decode_adaptive(z, setup.orders, setup.scheme)          # :591

@@ -158,3 +158,36 @@ def test_sharding_is_invariant(kat):
         other = link.run_fused(14.0, sigma, 900, seed=100, point=1)
         assert other.bit_errors != whole.bit_errors
         link.close()
+
+
+@pytest.mark.parametrize("n,chan,P,eq,fast", [(64, "Lin-Phoong_P2", 3, "ZF", True), (1024, "severe_multipath", 7, "MMSE", True),
+                                              (128, "rayleigh_fading", 5, "MMSE", False)])
+def test_applied_power_loading_replays_through_oracle(n, chan, P, eq, fast, kat):
+    """water-filling power APPLIED at the transmitter (sqrt(P_k) on every subcarrier) and compensated at
+    the receiver (1/sqrt(P_k)), as examples/waterfilling_noise_bump_experiment.py:148,165-169 does around the
+    reference's components; Simulation.run() itself never applies the allocation (simulation/models.py:508)."""
+    from ofdm_based_systems._native import Link
+    from ofdm_based_systems.simulation.sweep import LinkConfig
+    taps_raw, snr, order, n_ofdm = kat["chan_" + chan], 16.0, 16, 8
+    gains = np.abs(np.fft.fft(taps_raw, n)) ** 2
+    power = np.maximum(oc.waterfilling(1.0, gains, 10 ** (-snr / 10)) * n, 1e-4)      # mean power 1, floored
+    amp = np.sqrt(power)
+    rx_gain = 1.0 / amp
+    setup = oc.LinkSetup(n_sc=n, taps_raw=taps_raw, snr_db=snr, order=order, eq=eq, prefix_len_override=P, amp=amp,
+                         rx_gain=rx_gain)
+    cfg = LinkConfig(num_subcarriers=n, taps_raw=taps_raw, constellation_order=order, prefix_length=P, equalizator_type=eq,
+                     amp=amp, rx_gain=rx_gain)
+    link = Link(n, cfg.taps_chan, cfg.h_eq, cfg.orders, prefix_type="CYCLIC", prefix_len=P, equalizer=eq, amp=amp,
+                rx_gain=rx_gain)
+    assert link.uses_fast_kernel == fast
+    res, d = link.run_fused(snr, cfg.noise_sigma(snr), n_ofdm, seed=5, dump=("z", "rx_labels", "tx_labels", "noise"))
+    tx_bytes = pack_labels(d["tx_labels"], [4] * n)
+    ref = oc.run_link(setup, tx_bytes, n_ofdm * n * 4, noise=d["noise"].astype(np.complex128).reshape(-1))
+    z_ref = np.asarray(ref["received_symbols"]).reshape(n_ofdm, n)
+    assert np.max(np.abs(d["z"] - z_ref)) / np.max(np.abs(z_ref)) < 1e-5
+    mismatch = d["rx_labels"] != np.asarray(ref["rx_labels"]).reshape(n_ofdm, n)
+    assert not np.any(mismatch & (oc.qam_boundary_distance(z_ref, order) > 2e-4))
+    if not mismatch.any():
+        assert res.bit_errors == ref["bit_errors"] and res.symbol_errors == ref["symbol_errors"]
+    assert abs(res.papr_db - ref["papr_db"]) < 2e-4
+    link.close()
