@@ -87,8 +87,9 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   // at their team barriers and lose ~5 % to the extra one (N = 4096), so they run with SYNC = 0.
   // OFDM_B200_FAST_VARIANT=4 / =2 force SYNC = 0 / 2 for experiments.
   static const int variant = [] { const char* v = std::getenv("OFDM_B200_FAST_VARIANT"); return v ? std::atoi(v) : 0; }();
-  const bool free_running = variant == 4 || (variant != 2 && T > 32);
+  const bool free_running = variant == 4 || (variant != 2 && variant != 1 && T > 32);
   if (free_running) return launch_fast_kernel<E, T, false, false, 512, 0>(L, p, stream);
+  if (variant == 1) return launch_fast_kernel<E, T, false, false, 512, 1>(L, p, stream);
 #if OFDM_FAST_T == 32
   if (variant == 5) return launch_fast_kernel<E, T, false, false, 512, 4>(L, p, stream);
 #endif
