@@ -126,6 +126,10 @@ int ofdm_link_read_result(ofdm_link* link, void* stream, ofdm_link_result* out);
 /* device address of the raw counter block (8 x uint64, then double sum, then uint64 max bits): lets the
  * multi-GPU host side all-reduce the counters in place with NCCL */
 void* ofdm_link_counters_device_ptr(ofdm_link* link);
+/* Packs the link's counters into one row of the all-reduce payload (DEVICE memory, 9 + world doubles): 8 counters and
+ * the power sum as doubles (exact below 2^53), the power maximum in slot 9 + rank and zeros in the other ranks' slots,
+ * so that ONE SUM all-reduce combines counters, sums and maxima of all ranks.  Asynchronous on `stream`. */
+int ofdm_link_pack_counters(ofdm_link* link, double* payload_row_dev, int32_t rank, int32_t world, void* stream);
 /* kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t ofdm_b200_launch_count(void);
 

@@ -256,6 +256,13 @@ int read_counters(ofdm_link* L, cudaStream_t stream, ofdm_link_result* out) {
   return OFDM_OK;
 }
 
+__global__ void pack_counters_kernel(const CounterBlock* c, double* row, int rank, int world) {
+  const int i = threadIdx.x;
+  if (i < 8) row[i] = (double)c->cnt[i];
+  else if (i == 8) row[8] = c->power_sum;
+  else if (i < 9 + world) row[i] = (i - 9 == rank) ? __longlong_as_double((long long)c->power_max_bits) : 0.0;
+}
+
 __global__ void ffma_chain_kernel(float* out, int iters, float a, float b) {
   float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
         x7 = x0 + 7.f;
@@ -478,6 +485,16 @@ int ofdm_link_reset_counters(ofdm_link* L, void* stream) {
   if (!L) return fail(OFDM_EINVAL, "null link");
   DeviceGuard guard(L->device);
   CUDA_TRY(cudaMemsetAsync(L->d_cnt, 0, sizeof(CounterBlock), (cudaStream_t)stream));
+  return OFDM_OK;
+}
+
+int ofdm_link_pack_counters(ofdm_link* L, double* payload_row_dev, int32_t rank, int32_t world, void* stream) {
+  if (!L || !payload_row_dev) return fail(OFDM_EINVAL, "null argument");
+  if (world < 1 || world > 1000 || rank < 0 || rank >= world) return fail(OFDM_EINVAL, "rank %d of %d", rank, world);
+  DeviceGuard guard(L->device);
+  pack_counters_kernel<<<1, 9 + world + ((32 - (9 + world) % 32) % 32), 0, (cudaStream_t)stream>>>(L->d_cnt, payload_row_dev, rank, world);
+  count_launch();
+  CUDA_TRY(cudaGetLastError());
   return OFDM_OK;
 }
 

@@ -62,7 +62,7 @@ EXPORTS = (
     "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_create_loaded", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
     "ofdm_link_uses_fast_kernel",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
-    "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr",
+    "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr", "ofdm_link_pack_counters",
     "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev", "ofdm_frames_run",
 )
 
@@ -95,6 +95,7 @@ def _load() -> C.CDLL:
     lib.ofdm_link_reset_counters.argtypes = [vp, vp]
     lib.ofdm_link_read_result.argtypes = [vp, vp, C.POINTER(LinkResult)]
     lib.ofdm_link_counters_device_ptr.argtypes = [vp]
+    lib.ofdm_link_pack_counters.argtypes = [vp, vp, i32, i32, vp]
     lib.ofdm_link_counters_device_ptr.restype = vp
     lib.ofdm_waterfill_bitload_batched.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     lib.ofdm_waterfill_bitload_batched_dev.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
@@ -261,6 +262,9 @@ class Link:
         res = LinkResult()
         _check(lib.ofdm_link_read_result(self._h, stream, C.byref(res)))
         return LinkCounters.from_struct(res)
+
+    def pack_counters(self, payload_row_dev: int, rank: int, world: int, stream: int = 0) -> None:
+        _check(lib.ofdm_link_pack_counters(self._h, payload_row_dev, rank, world, stream))
 
     @property
     def counters_device_ptr(self) -> int:

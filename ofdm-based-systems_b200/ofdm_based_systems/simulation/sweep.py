@@ -145,9 +145,11 @@ class LinkSweep:
         return first, base + (1 if rank < rem else 0)
 
     def enqueue(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
-                weak_scaling: bool = False):
-        """Queue every SNR point on the current CUDA stream, then ONE all-reduce; nothing is read back.
-        Returns the device tensor [points, 9 + world] (float64) that ``finalize`` decodes."""
+                weak_scaling: bool = False, kernel_events=None):
+        """Queue every SNR point on the current CUDA stream - per point a counter reset (memset), the link kernel
+        and a one-block pack of the counters into the all-reduce payload - then ONE all-reduce; nothing is read
+        back.  Returns the device tensor [points, 9 + world] (float64) that ``finalize`` decodes.
+        ``kernel_events``: optional (start, end) torch CUDA events recorded around the link kernel of point 0."""
         import torch
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized()
@@ -159,15 +161,20 @@ class LinkSweep:
             first, count = self.shard(n_symbols, rank, world)
         dev = torch.device("cuda", torch.cuda.current_device())
         stream = torch.cuda.current_stream().cuda_stream
-        block = torch.as_tensor(_DeviceWords(self.link.counters_device_ptr, N_WORDS), device=dev)
-        k = len(snr_dbs)
-        rows = torch.empty((k, N_WORDS), dtype=torch.int64, device=dev)
+        payload = torch.empty((len(snr_dbs), 9 + world), dtype=torch.float64, device=dev)
+        row_bytes = payload.stride(0) * payload.element_size()
         for i, snr in enumerate(snr_dbs):
-            block.zero_()
+            self.link.reset_counters(stream)
+            if kernel_events is not None and i == 0:
+                kernel_events[0].record()
             self.link.launch_fused(float(snr), self.cfg.noise_sigma(float(snr)), count, seed=seed, point=i,
                                    first_symbol=first, stream=stream)
-            rows[i].copy_(block)
-        return combine_counters(rows, rank, world, group if distributed else None)
+            if kernel_events is not None and i == 0:
+                kernel_events[1].record()
+            self.link.pack_counters(payload.data_ptr() + i * row_bytes, rank, world, stream)
+        if world > 1:
+            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group if distributed else None)
+        return payload
 
     def finalize(self, snr_dbs: Sequence[float], payload) -> List[dict]:
         """Device -> host read of the combined counters; result keys follow the reference's result dict

@@ -154,3 +154,24 @@ def test_published_short_prefix_table(prefix, ratio, kat):
     sweep.close()
     assert got["total_bits"] == 80_000 * 384
     assert abs(got["bit_error_rate"] - PUBLISHED_MMSE_30DB[(prefix, P)]) < 1e-3, (P, got["bit_error_rate"])
+
+
+def test_device_side_sweep_equals_synchronous_sweep(kat):
+    """The multi-GPU path (reset -> kernel -> pack -> all-reduce payload on the current stream) and the one-GPU
+    synchronous path return the same counters."""
+    import torch
+    from ofdm_based_systems.simulation.sweep import LinkConfig, LinkSweep
+    cfg = LinkConfig(num_subcarriers=256, taps_raw=kat["chan_rayleigh_fading"], constellation_order=16, prefix_length=5,
+                     equalizator_type="MMSE")
+    sweep = LinkSweep(cfg)
+    snrs = [8.0, 14.0, 20.0]
+    a = sweep.sweep(snrs, 3000, seed=9)
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    b = sweep.finalize(snrs, sweep.enqueue(snrs, 3000, seed=9, kernel_events=ev))
+    torch.cuda.synchronize()
+    assert ev[0].elapsed_time(ev[1]) > 0
+    for x, y in zip(a, b):
+        for key in ("bit_errors", "total_bits", "symbol_errors", "num_ofdm_symbols"):
+            assert x[key] == y[key]
+        assert abs(x["papr_db"] - y["papr_db"]) < 1e-9
+    sweep.close()
