@@ -1,50 +1,19 @@
-"""String enums of the simulation schema; values and names follow the reference's
-configuration/enums.py:4-67 so that the shipped config/*.json files load unchanged."""
-from enum import Enum
+"""String enums of the simulation schema.  Member names and values are those the shipped config/*.json files and
+the reference's callers use (its configuration/enums.py); ``str(member)`` is the JSON value."""
+import enum
 
 
-class _StrEnum(str, Enum):
-    def __str__(self) -> str:
-        return self.value
+def _json_enum(name: str, **members: str):
+    cls = enum.Enum(name, members, type=str, module=__name__)
+    cls.__str__ = lambda self: self.value
+    return cls
 
 
-class ConstellationType(_StrEnum):
-    QAM = "QAM"
-    PSK = "PSK"
-
-
-class PrefixType(_StrEnum):
-    CYCLIC = "CYCLIC"
-    ZERO = "ZERO"
-    NONE = "NONE"
-
-
-class EqualizationMethod(_StrEnum):
-    ZF = "ZF"
-    MMSE = "MMSE"
-    NONE = "NONE"
-
-
-class ModulationType(_StrEnum):
-    OFDM = "OFDM"
-    SC_OFDM = "SC-OFDM"
-
-
-class ChannelType(_StrEnum):
-    FLAT = "FLAT"      # quirk Q4: means "the built-in 4-tap default", not a flat channel
-    CUSTOM = "CUSTOM"
-
-
-class NoiseType(_StrEnum):
-    AWGN = "AWGN"
-    NONE = "NONE"
-
-
-class PowerAllocationType(_StrEnum):
-    UNIFORM = "UNIFORM"
-    WATERFILLING = "WATERFILLING"
-
-
-class AdaptiveModulationMode(_StrEnum):
-    FIXED = "FIXED"
-    CAPACITY_BASED = "CAPACITY_BASED"
+ConstellationType = _json_enum("ConstellationType", QAM="QAM", PSK="PSK")
+PrefixType = _json_enum("PrefixType", CYCLIC="CYCLIC", ZERO="ZERO", NONE="NONE")
+EqualizationMethod = _json_enum("EqualizationMethod", ZF="ZF", MMSE="MMSE", NONE="NONE")
+ModulationType = _json_enum("ModulationType", OFDM="OFDM", SC_OFDM="SC-OFDM")
+ChannelType = _json_enum("ChannelType", FLAT="FLAT", CUSTOM="CUSTOM")   # FLAT = the built-in 4-tap default (quirk Q4)
+NoiseType = _json_enum("NoiseType", AWGN="AWGN", NONE="NONE")
+PowerAllocationType = _json_enum("PowerAllocationType", UNIFORM="UNIFORM", WATERFILLING="WATERFILLING")
+AdaptiveModulationMode = _json_enum("AdaptiveModulationMode", FIXED="FIXED", CAPACITY_BASED="CAPACITY_BASED")

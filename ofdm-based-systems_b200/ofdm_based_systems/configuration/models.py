@@ -1,15 +1,16 @@
-"""pydantic schema of config/settings.json and config/simulation_settings*.json
-(reference: configuration/models.py:19-151).  Unknown keys such as ``capacity_scaling_factor`` are
-ignored, exactly as pydantic's default does for the reference."""
+"""Settings schema of config/settings.json and config/simulation_settings*.json.
+
+The field names, defaults and validation messages are the contract of the shipped JSON files and of the reference's
+callers (its configuration/models.py); the models themselves are generated from the tables below with
+``pydantic.create_model``.  Unknown JSON keys such as ``capacity_scaling_factor`` are ignored (pydantic's default).
+"""
 import json
 import os
 from typing import Optional
 
-from pydantic import BaseModel, Field, field_validator
+from pydantic import BaseModel, create_model, field_validator
 
-from ofdm_based_systems.configuration.enums import (
-    AdaptiveModulationMode, ChannelType, ConstellationType, EqualizationMethod, ModulationType, NoiseType,
-    PowerAllocationType, PrefixType)
+from ofdm_based_systems.configuration import enums as E
 
 
 class BaseSettings(BaseModel):
@@ -20,81 +21,107 @@ class BaseSettings(BaseModel):
         with open(file_path, "r", encoding="utf-8") as fh:
             return cls(**json.load(fh))
 
+    # (label, attribute, quote the value, only when not None) rows printed by __str__
+    _report = ()
 
-class Settings(BaseSettings):
-    project_name: str = Field(..., description="The name of the project")
-    version: str = Field(..., description="The version of the project")
-    debug: bool = Field(False, description="Enable or disable debug mode")
+    def __str__(self):
+        rows = []
+        for label, attr, quoted, optional in self._report:
+            value = getattr(self, attr)
+            if optional and value is None:
+                continue
+            rows.append(f"{label}: '{value}'" if quoted else f"{label}: {value}")
+        return "\n".join(rows)
 
+
+def _one_of_bits_or_symbols(cls, v, info):
+    bits = info.data.get("num_bits")
+    if (bits is None) == (v is None):
+        raise ValueError("Either num_bits or num_symbols must be specified." if v is None
+                         else "Only one of num_bits or num_symbols should be specified.")
+    return v
+
+
+def _ratio_in_range(cls, v):
+    if not 0.0 <= v <= 2.0:
+        raise ValueError("prefix_length_ratio must be between 0 and 1 (inclusive).")
+    return v
+
+
+def _order_bound(cls, v):
+    if not 2 <= v <= 4096:
+        raise ValueError("Constellation order must be between 2 and 4096.")
+    if v & (v - 1):
+        raise ValueError(f"Constellation order must be a power of 2, got {v}.")
+    return v
+
+
+def _target_ser(cls, v):
+    if v <= 0:
+        raise ValueError("desired_symbol_error_rate must be positive.")
+    if v >= 0.5:
+        raise ValueError("desired_symbol_error_rate must be less than 0.5.")
+    return v
+
+
+def _validator(fn, *fields):
+    return field_validator(*fields)(classmethod(fn))
+
+
+class _SettingsText(BaseSettings):
     def __str__(self):
         return f"{self.project_name}\n{self.version}\nDebug Mode: {self.debug}"
 
 
-class SimulationSettings(BaseSettings):
-    num_bands: int = Field(..., description="Number of frequency bands")
-    signal_noise_ratios: list[float] = Field(..., description="List of signal-to-noise ratios for simulation")
-    channel_model_path: str = Field(..., description="Path to the channel model file")
-    channel_type: ChannelType = Field(ChannelType.FLAT, description="Type of the channel (e.g., FLAT or CUSTOM)")
-    noise_type: NoiseType = Field(NoiseType.AWGN, description="Type of noise to be added (e.g., AWGN, NONE)")
-    num_bits: Optional[int] = Field(None, description="Number of bits to simulate")
-    num_symbols: Optional[int] = Field(None, description="Number of symbols to simulate")
-    constellation_order: int = Field(16, description="Order of the QAM constellation (e.g., 4, 16, 64)")
-    constellation_type: ConstellationType = Field(ConstellationType.PSK, description="Type of the constellation")
-    prefix_type: PrefixType = Field(PrefixType.CYCLIC, description="Type of cyclic prefix (e.g., CYCLIC or ZERO)")
-    prefix_length_ratio: float = Field(0.25, description="Ratio of cyclic prefix length to channel time domain size")
-    equalization_method: EqualizationMethod = Field(EqualizationMethod.MMSE, description="Equalization method")
-    modulation_type: ModulationType = Field(ModulationType.OFDM, description="Type of modulation")
-    power_allocation_type: PowerAllocationType = Field(PowerAllocationType.UNIFORM, description="Power allocation")
-    adaptive_modulation_mode: AdaptiveModulationMode = Field(AdaptiveModulationMode.FIXED, description="Adaptive mode")
-    min_constellation_order: int = Field(4, description="Minimum constellation order for adaptive modulation")
-    max_constellation_order: int = Field(256, description="Maximum constellation order for adaptive modulation")
-    desired_symbol_error_rate: float = Field(1e-3, description="Desired symbol error rate for adaptive modulation")
+Settings = create_model("Settings", __base__=_SettingsText, __module__=__name__,
+                        project_name=(str, ...), version=(str, ...), debug=(bool, False))
 
-    def __str__(self):
-        lines = [f"Number of Bands: {self.num_bands}", f"Signal-to-Noise Ratios: {self.signal_noise_ratios}",
-                 f"Channel Type: {self.channel_type}", f"Channel Model Path: '{self.channel_model_path}'",
-                 f"Noise Type: {self.noise_type}"]
-        if self.num_bits is not None:
-            lines.append(f"Number of Bits: {self.num_bits}")
-        if self.num_symbols is not None:
-            lines.append(f"Number of Symbols: {self.num_symbols}")
-        lines += [f"Constellation Type: '{self.constellation_type}'", f"Constellation Order: {self.constellation_order}",
-                  f"Prefix Type: {self.prefix_type}", f"Prefix Length Ratio: {self.prefix_length_ratio}",
-                  f"Equalization Method: {self.equalization_method}", f"Modulation Type: {self.modulation_type}",
-                  f"Power Allocation Type: {self.power_allocation_type}"]
-        return "\n".join(lines)
 
-    @field_validator("num_symbols")
-    @classmethod
-    def check_bits_or_symbols(cls, v, info):
-        bits = info.data.get("num_bits")
-        if bits is None and v is None:
-            raise ValueError("Either num_bits or num_symbols must be specified.")
-        if bits is not None and v is not None:
-            raise ValueError("Only one of num_bits or num_symbols should be specified.")
-        return v
+class _SimulationText(BaseSettings):
+    _report = (("Number of Bands", "num_bands", False, False),
+               ("Signal-to-Noise Ratios", "signal_noise_ratios", False, False),
+               ("Channel Type", "channel_type", False, False),
+               ("Channel Model Path", "channel_model_path", True, False),
+               ("Noise Type", "noise_type", False, False),
+               ("Number of Bits", "num_bits", False, True),
+               ("Number of Symbols", "num_symbols", False, True),
+               ("Constellation Type", "constellation_type", True, False),
+               ("Constellation Order", "constellation_order", False, False),
+               ("Prefix Type", "prefix_type", False, False),
+               ("Prefix Length Ratio", "prefix_length_ratio", False, False),
+               ("Equalization Method", "equalization_method", False, False),
+               ("Modulation Type", "modulation_type", False, False),
+               ("Power Allocation Type", "power_allocation_type", False, False))
 
-    @field_validator("prefix_length_ratio")
-    @classmethod
-    def validate_prefix_length_ratio(cls, v):
-        if not 0.0 <= v <= 2.0:
-            raise ValueError("prefix_length_ratio must be between 0 and 1 (inclusive).")
-        return v
 
-    @field_validator("min_constellation_order", "max_constellation_order")
-    @classmethod
-    def validate_constellation_order(cls, v):
-        if v < 2 or v > 4096:
-            raise ValueError("Constellation order must be between 2 and 4096.")
-        if v & (v - 1):
-            raise ValueError(f"Constellation order must be a power of 2, got {v}.")
-        return v
-
-    @field_validator("desired_symbol_error_rate")
-    @classmethod
-    def validate_desired_symbol_error_rate(cls, v):
-        if v <= 0:
-            raise ValueError("desired_symbol_error_rate must be positive.")
-        if v >= 0.5:
-            raise ValueError("desired_symbol_error_rate must be less than 0.5.")
-        return v
+SimulationSettings = create_model(
+    "SimulationSettings", __base__=_SimulationText, __module__=__name__,
+    __validators__={
+        "check_bits_or_symbols": _validator(_one_of_bits_or_symbols, "num_symbols"),
+        "validate_prefix_length_ratio": _validator(_ratio_in_range, "prefix_length_ratio"),
+        "validate_constellation_order": _validator(_order_bound, "min_constellation_order", "max_constellation_order"),
+        "validate_desired_symbol_error_rate": _validator(_target_ser, "desired_symbol_error_rate"),
+    },
+    # ---- what is simulated
+    num_bands=(int, ...),
+    signal_noise_ratios=(list[float], ...),
+    num_bits=(Optional[int], None),
+    num_symbols=(Optional[int], None),
+    # ---- channel and noise
+    channel_model_path=(str, ...),
+    channel_type=(E.ChannelType, E.ChannelType.FLAT),
+    noise_type=(E.NoiseType, E.NoiseType.AWGN),
+    # ---- waveform
+    constellation_order=(int, 16),
+    constellation_type=(E.ConstellationType, E.ConstellationType.PSK),
+    modulation_type=(E.ModulationType, E.ModulationType.OFDM),
+    prefix_type=(E.PrefixType, E.PrefixType.CYCLIC),
+    prefix_length_ratio=(float, 0.25),
+    equalization_method=(E.EqualizationMethod, E.EqualizationMethod.MMSE),
+    # ---- loading
+    power_allocation_type=(E.PowerAllocationType, E.PowerAllocationType.UNIFORM),
+    adaptive_modulation_mode=(E.AdaptiveModulationMode, E.AdaptiveModulationMode.FIXED),
+    min_constellation_order=(int, 4),
+    max_constellation_order=(int, 256),
+    desired_symbol_error_rate=(float, 1e-3),
+)

@@ -1,26 +1,21 @@
-"""Noise models (reference: noise/models.py:6-27).  In the fused CUDA mode the same sigma^2 rule is
-applied with Philox/Box-Muller samples generated in registers."""
-from abc import ABC, abstractmethod
+"""Noise-model shells.  In the fused CUDA mode the same sigma^2 rule (``_chain.awgn``) is applied to Philox /
+Box-Muller samples generated in registers; replay mode records what these classes add."""
+import abc
 
-import numpy as np
-from numpy.typing import NDArray
+from ofdm_based_systems import _chain
 
 
-class INoiseModel(ABC):
-    @abstractmethod
-    def add_noise(self, signal: NDArray[np.complex128], snr_db: float) -> NDArray[np.complex128]:
-        ...
+class INoiseModel(abc.ABC):
+    @abc.abstractmethod
+    def add_noise(self, signal, snr_db):
+        """signal + noise for the given SNR (dB) of the measured stream power"""
 
 
 class AWGNoiseModel(INoiseModel):
-    def add_noise(self, signal: NDArray[np.complex128], snr_db: float) -> NDArray[np.complex128]:
-        # sigma^2 from the MEASURED stream power; legacy global RNG, real part drawn first
-        sigma2 = np.mean(np.abs(signal) ** 2) / (10 ** (snr_db / 10))
-        re = np.random.normal(size=signal.shape)
-        im = np.random.normal(size=signal.shape)
-        return signal + np.sqrt(sigma2 / 2) * (re + 1j * im)
+    def add_noise(self, signal, snr_db):
+        return _chain.awgn(signal, snr_db)
 
 
 class NoNoiseModel(INoiseModel):
-    def add_noise(self, signal: NDArray[np.complex128], snr_db: float) -> NDArray[np.complex128]:
-        return signal
+    def add_noise(self, signal, snr_db):
+        return signal            # the input object itself
