@@ -1,0 +1,95 @@
+"""Edge cases of the C ABI on the GPU: empty ranges, ragged recorded streams, argument errors, 64-bit symbol
+indices, and size-independent properties at BASELINE.json's full sizes (linearity of the counters in the symbol
+range, noiseless links decode without error, counters scale with the bits processed)."""
+import numpy as np
+import pytest
+
+import ofdm_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+
+def headline_link(order=64, n=1024, eq="MMSE", **kw):
+    from ofdm_based_systems._native import Link
+    taps = oc.normalize_taps(np.load(__import__("os").path.join(__import__("conftest").ROOT, "config", "channel_models",
+                                                                    "severe_multipath.npy")))
+    return Link(n, taps, np.fft.fft(taps, n), np.full(n, order), prefix_type="CYCLIC", prefix_len=7, equalizer=eq, **kw)
+
+
+def test_empty_symbol_range_and_zero_noise():
+    link = headline_link()
+    r = link.run_fused(20.0, 0.1, 0)
+    assert (r.bits, r.bit_errors, r.symbols, r.ofdm_symbols, r.tx_samples) == (0, 0, 0, 0, 0)
+    assert r.papr_db == float("inf")
+    r = link.run_fused(200.0, 0.0, 500, seed=3)                     # noiseless: every decision is right
+    assert r.bits == 500 * 6144 and r.bit_errors == 0 and r.symbol_errors == 0
+    assert 8.0 < r.papr_db < 16.0
+    link.close()
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+def test_ragged_recorded_stream(kernel, monkeypatch):
+    """A recorded byte stream that ends inside the last OFDM symbol: positions past compare_limit_bits are not compared
+    (zip() truncation, simulation/models.py:597); the missing bits transmit as zeros."""
+    if kernel == "general":
+        monkeypatch.setenv("OFDM_B200_FORCE_GENERAL", "1")
+    link = headline_link(order=16)
+    rng = np.random.default_rng(5)
+    n_sym, bits_per = 5, 4096
+    full = rng.integers(0, 256, n_sym * bits_per // 8, dtype=np.uint8)
+    cut = full[: len(full) - 100]                                     # 800 bits short
+    noise = (rng.normal(size=n_sym * 1031) + 1j * rng.normal(size=n_sym * 1031)) * 0.05
+    whole = link.run_replay(20.0, full.tobytes(), noise, n_sym)
+    ragged = link.run_replay(20.0, cut.tobytes(), noise, n_sym, compare_limit_bits=8 * len(cut))
+    assert whole.bits == n_sym * bits_per and ragged.bits == 8 * len(cut)
+    assert ragged.bit_errors <= whole.bit_errors + 40                 # the zero-filled tail changes only the last symbol
+    none = link.run_replay(20.0, full.tobytes(), None, n_sym)
+    assert none.bit_errors == 0
+    with pytest.raises(ValueError):
+        link.run_replay(20.0, full.tobytes(), noise[:-1], n_sym)
+    with pytest.raises(ValueError):
+        link.run_replay(20.0, full.tobytes(), noise.real.copy(), n_sym)
+    link.close()
+
+
+def test_argument_errors_come_back_as_value_errors():
+    from ofdm_based_systems._native import Link
+    h = np.ones(1, complex)
+    ok = dict(prefix_type="CYCLIC", prefix_len=0)
+    with pytest.raises(ValueError, match="power of two"):
+        Link(100, h, np.ones(100, complex), np.full(100, 4), **ok)
+    with pytest.raises(ValueError, match="perfect square"):
+        Link(64, h, np.ones(64, complex), np.full(64, 8), **ok)
+    with pytest.raises(ValueError, match="n_taps"):
+        Link(64, np.ones(33, complex), np.ones(64, complex), np.full(64, 4), **ok)
+    with pytest.raises(ValueError, match="prefix NONE"):
+        Link(64, h, np.ones(64, complex), np.full(64, 4), prefix_type="NONE", prefix_len=3)
+    with pytest.raises(ValueError, match="one entry per subcarrier"):
+        Link(64, h, np.ones(63, complex), np.full(64, 4), **ok)
+    with pytest.raises(ValueError, match="No active subcarriers"):
+        Link(64, h, np.ones(64, complex), np.zeros(64, int), **ok).run_fused(10.0, 0.1, 4)
+    with pytest.raises(KeyError):
+        Link(64, h, np.ones(64, complex), np.full(64, 4), prefix_type="BOGUS")
+
+
+@pytest.mark.parametrize("n,order,per_launch", [(1024, 16, 244_141), (4096, 256, 30_518)])
+def test_full_size_counters_are_additive_and_reproducible(n, order, per_launch):
+    """BASELINE configs #2 / #5 at 1e9 bits per point: the counters of [0, S) equal the sum over a 3-way split
+    (what sharding over GPUs relies on), a re-run reproduces them exactly, 64-bit symbol indices work."""
+    link = headline_link(order=order, n=n)
+    bps = oc.bits_per_symbol(order)
+    sigma = float(np.sqrt(1 / 10 ** 2.4 / 2))
+    whole = link.run_fused(24.0, sigma, per_launch, seed=42, point=3)
+    assert whole.bits == per_launch * n * bps >= 10 ** 9
+    again = link.run_fused(24.0, sigma, per_launch, seed=42, point=3)
+    assert (again.bit_errors, again.symbol_errors, again.tx_power_max) == (whole.bit_errors, whole.symbol_errors, whole.tx_power_max)
+    cuts = [0, per_launch // 3, per_launch // 3 * 2 + 1, per_launch]
+    parts = [link.run_fused(24.0, sigma, b - a, seed=42, point=3, first_symbol=a) for a, b in zip(cuts, cuts[1:])]
+    assert whole.bit_errors == sum(p.bit_errors for p in parts) > 0
+    assert whole.symbol_errors == sum(p.symbol_errors for p in parts)
+    far = link.run_fused(24.0, sigma, 2000, seed=42, point=3, first_symbol=(1 << 40) + 7)
+    assert far.bits == 2000 * n * bps and 0 < far.bit_errors < far.bits // 4
+    # BER of the two halves agree within their sampling noise (per-symbol correlated errors: generous 6 sigma)
+    ber = [p.bit_errors / p.bits for p in parts]
+    assert max(ber) - min(ber) < 6 * np.sqrt(max(ber) / (parts[0].bits / (n * bps))) + 1e-9
+    link.close()
