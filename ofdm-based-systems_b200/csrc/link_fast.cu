@@ -14,7 +14,9 @@ int launch_frames_shape(int sms, const FastParams& p, cudaStream_t stream);
 int launch_fast_frames(int n_subcarriers, int sms, const FastParams& p, cudaStream_t stream) {
   switch (n_subcarriers) {
     case 64: return launch_frames_shape<8, 8>(sms, p, stream);
+    case 128: return launch_frames_shape<8, 16>(sms, p, stream);
     case 256: return launch_frames_shape<16, 16>(sms, p, stream);
+    case 512: return launch_frames_shape<16, 32>(sms, p, stream);
     case 1024: return launch_frames_shape<32, 32>(sms, p, stream);
     case 2048: return launch_frames_shape<32, 64>(sms, p, stream);
     case 4096: return launch_frames_shape<32, 128>(sms, p, stream);
@@ -22,13 +24,15 @@ int launch_fast_frames(int n_subcarriers, int sms, const FastParams& p, cudaStre
   }
 }
 
-bool fast_supports_n(int n) { return n == 64 || n == 256 || n == 1024 || n == 2048 || n == 4096; }
-int fast_samples_per_lane(int n) { return n == 64 ? 8 : n == 256 ? 16 : 32; }
+bool fast_supports_n(int n) { return n >= 64 && n <= 4096 && (n & (n - 1)) == 0; }
+int fast_samples_per_lane(int n) { return n <= 128 ? 8 : n <= 512 ? 16 : 32; }
 
 int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, cudaStream_t stream) {
   switch (L->d.n_subcarriers) {
     case 64: return launch_fast_shape<8, 8>(L, p, dump, replay, adapt, stream);
+    case 128: return launch_fast_shape<8, 16>(L, p, dump, replay, adapt, stream);
     case 256: return launch_fast_shape<16, 16>(L, p, dump, replay, adapt, stream);
+    case 512: return launch_fast_shape<16, 32>(L, p, dump, replay, adapt, stream);
     case 1024: return launch_fast_shape<32, 32>(L, p, dump, replay, adapt, stream);
     case 2048: return launch_fast_shape<32, 64>(L, p, dump, replay, adapt, stream);
     case 4096: return launch_fast_shape<32, 128>(L, p, dump, replay, adapt, stream);

@@ -2,8 +2,8 @@
 //   OFDM modulator, square QAM of one order on every subcarrier (4 .. 256), cyclic prefix at least as long
 //   as the channel memory (no inter-symbol interference) and at most E samples, <= 8 taps, Philox bits and
 //   noise, N = E*T subcarriers: a team of T lanes with E samples per lane.  T = E in {8, 16, 32}
-//   (N = 64, 256, 1024: two-pass transform, the team fits one warp); T = 2E or 4E with E = 32 (N = 2048, 4096:
-//   the team spans 2 or 4 warps, a third radix-2/4 pass follows a second exchange).
+//   (N = 64, 256, 1024: two-pass transform); T = 2E or 4E (N = 128, 512 inside a warp; N = 2048, 4096 with a team
+//   of 2 or 4 warps): a third radix-2/4 pass follows a second exchange.
 // Same chain and same reference lines as link_kernel.cuh; what differs is the machine mapping:
 //   * a team of E lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers;
 //   * ONE forward-FFT body serves both transforms (the IFFT runs as an FFT on re/im-swapped data) and the
@@ -82,7 +82,7 @@ struct FastParams {
 
 template <int E, int T_ = E, int BLOCK_ = 512>
 struct FastGeometry {
-  static_assert(T_ % E == 0 && (T_ == E || E == 32), "team = whole warps when it is wider than E");
+  static_assert(T_ % E == 0 && (T_ / E == 1 || T_ / E == 2 || T_ / E == 4) && (T_ <= 32 || T_ % 32 == 0), "team shape");
   static constexpr int T = T_;                // lanes per OFDM symbol
   static constexpr int N = E * T;
   static constexpr int W = T / E;             // radix of the third pass (1: two-pass transform)
@@ -93,7 +93,7 @@ struct FastGeometry {
   static constexpr int TW2_F2 = (E - 1) * E;  // pass-2 twiddles (float2)
   static constexpr int TW3_F2 = W > 1 ? N / W : 0;
   static constexpr int TW_F2 = TW2_F2 + TW3_F2;
-  static constexpr int RED_F = W > 1 ? TEAMS * W : 0;   // cross-warp reduction scratch (floats)
+  static constexpr int RED_F = T > 32 ? TEAMS * (T / 32) : 0;   // cross-warp reduction scratch (floats)
   static constexpr size_t SMEM_BYTES =
       (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) + RED_F * sizeof(float);
 };
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   float2* row = buf + t * RS;
   float2* s_tw = smem2 + size_t(G::TEAMS) * G::TEAM_F2;
   float4* s_eq = reinterpret_cast<float4*>(s_tw + G::TW_F2);
-  float* s_red = reinterpret_cast<float*>(s_eq + N) + team_in_block * W;
+  float* s_red = reinterpret_cast<float*>(s_eq + N) + team_in_block * (T / 32);
   float2* col = buf + trow * RS + tcol;   // strided set: col[W * RS * m]
   auto tsync = [&]() { team_sync<T>(team_in_block); };
 
@@ -559,12 +559,12 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
 #pragma unroll
         for (int off = (T < 32 ? T : 32) / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-        if constexpr (W > 1) {
-          if (lane == 0) s_red[trow] = ss;
+        if constexpr (T > 32) {   // the team spans T / 32 warps
+          if (lane == 0) s_red[t / 32] = ss;
           tsync();
           ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < W; ++i) ss += s_red[i];
+          for (int i = 0; i < T / 32; ++i) ss += s_red[i];
         }
         const float sigma2 = ss * mmse_c;
         unsigned rxc[WORDS], rxr[WORDS];

@@ -25,7 +25,8 @@ def single_link(n, taps_raw, orders, P, eq, snr, S, seed, point, first_symbol):
     return res
 
 
-@pytest.mark.parametrize("n,order,eq,S", [(64, 16, "ZF", 100), (256, 64, "MMSE", 37), (1024, 64, "MMSE", 20), (4096, 256, "MMSE", 9)])
+@pytest.mark.parametrize("n,order,eq,S", [(64, 16, "ZF", 100), (128, 4, "MMSE", 70), (256, 64, "MMSE", 37), (512, 16, "NONE", 33), (1024, 64, "MMSE", 20),
+                                          (4096, 256, "MMSE", 9)])
 def test_fixed_order_frames_reproduce_single_links(n, order, eq, S):
     from ofdm_based_systems._native import run_frames
     rng = np.random.default_rng(n)
@@ -89,7 +90,7 @@ def test_frames_shard_like_symbols():
     again = run_frames(1024, 1, 4000, 20.0, n_taps=8, order=64, seed=5, first_frame=1)
     assert few["frames"][1].bit_errors == again["frames"][0].bit_errors > 0
     with pytest.raises(ValueError):
-        run_frames(128, 2, 10, 20.0, order=16)
+        run_frames(96, 2, 10, 20.0, order=16)
     with pytest.raises(ValueError):
         run_frames(256, 2, 10, 20.0, max_order=1024)
 

@@ -17,6 +17,8 @@ CASES = [
     ("c5", 4096, 256, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 30.0, "OFDM", 9),
     ("n2048", 2048, 64, "QAM", "rayleigh_fading", "CYCLIC", 5, "MMSE", 24.0, "OFDM", 11),
     ("n2048zf", 2048, 16, "QAM", "severe_multipath", "CYCLIC", 64, "ZF", 14.0, "OFDM", 5),
+    ("n128", 128, 16, "QAM", "rayleigh_fading", "CYCLIC", 5, "MMSE", 17.0, "OFDM", 30),
+    ("n512", 512, 256, "QAM", "severe_multipath", "CYCLIC", 9, "ZF", 30.0, "OFDM", 12),
     ("zp", 256, 16, "QAM", "rayleigh_fading", "ZERO", 5, "MMSE", 15.0, "OFDM", 16),
     ("isi", 128, 64, "QAM", "severe_multipath", "CYCLIC", 2, "ZF", 24.0, "OFDM", 40),
     ("none", 64, 16, "QAM", "Lin-Phoong_P2", "NONE", 0, "MMSE", 22.0, "OFDM", 48),
@@ -49,7 +51,7 @@ def test_fused_dump_replays_through_oracle(case, kat):
     sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
     link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
                 modulator=modulator, equalizer=eq, scheme=scheme)
-    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf"))
+    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512"))
     # with inter-symbol interference the oracle's stream must start where the kernel's does (zero history)
     first = 0 if len(taps_raw) - 1 > P else 1000
     res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=first,
@@ -76,7 +78,9 @@ ADAPTIVE_CASES = [
     ("a256", 256, "severe_multipath", 7, "ZF", 26.0, 24, True),
     ("a1024", 1024, "severe_multipath", 7, "MMSE", 22.0, 8, True),
     ("a4096", 4096, "rayleigh_fading", 5, "MMSE", 28.0, 8, True),
-    ("a128", 128, "two_ray", 1, "MMSE", 20.0, 32, False),
+    ("a128", 128, "two_ray", 1, "MMSE", 20.0, 32, True),
+    ("a512", 512, "Lin-Phoong_P2", 3, "ZF", 25.0, 16, True),
+    ("a8192", 8192, "two_ray", 1, "MMSE", 20.0, 2, False),
 ]
 
 
@@ -161,7 +165,7 @@ def test_sharding_is_invariant(kat):
 
 
 @pytest.mark.parametrize("n,chan,P,eq,fast", [(64, "Lin-Phoong_P2", 3, "ZF", True), (1024, "severe_multipath", 7, "MMSE", True),
-                                              (128, "rayleigh_fading", 5, "MMSE", False)])
+                                              (128, "rayleigh_fading", 5, "MMSE", True), (8192, "two_ray", 1, "ZF", False)])
 def test_applied_power_loading_replays_through_oracle(n, chan, P, eq, fast, kat):
     """water-filling power APPLIED at the transmitter (sqrt(P_k) on every subcarrier) and compensated at
     the receiver (1/sqrt(P_k)), as examples/waterfilling_noise_bump_experiment.py:148,165-169 does around the
