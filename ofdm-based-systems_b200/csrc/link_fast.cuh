@@ -108,18 +108,15 @@ __device__ __forceinline__ void team_sync(int team_in_block) {
   }
 }
 
-// SYNC = 0: warps run free.  SYNC = 1: __syncthreads() at the section boundaries.  SYNC >= 2: named barrier
-// among the warps that share a scheduler (warp id mod 4); SYNC = 3 also inside the FIR loop; SYNC = 4: named
-// barrier among groups of 4 consecutive warps (one per scheduler).
+// Alignment of the warps of a block at the section boundaries of the symbol loop (transmitter, channel, receiver):
+// SYNC = 0: warps run free.  SYNC = 1: __syncthreads().  SYNC = 2: named barrier among the warps that share a
+// scheduler (warp id mod 4), so that they fetch the same instruction-cache lines.  (Grouping one warp per scheduler
+// instead - so that every scheduler mixes FMA-heavy, Philox and MUFU sections - was measured 1.3 % slower.)
 template <int SYNC, int BLOCK>
 __device__ __forceinline__ void section_sync() {
   if constexpr (SYNC == 1) {
     __syncthreads();
-  } else if constexpr (SYNC == 4) {
-    // groups of 4 consecutive warps = one warp per scheduler: every scheduler then hosts warps of BLOCK/128
-    // different groups, which drift into different sections (FMA-heavy, Philox, MUFU) and mix on the pipes
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + (threadIdx.x >> 7)), "n"(128) : "memory");
-  } else if constexpr (SYNC >= 2) {
+  } else if constexpr (SYNC == 2) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + ((threadIdx.x >> 5) & 3)), "n"(BLOCK / 4) : "memory");
   }
 }
@@ -396,7 +393,6 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         tsync();
 #pragma unroll FIR_UNROLL
         for (int c = 0; c < E / 8; ++c) {
-          if constexpr (SYNC >= 3) section_sync<SYNC, BLOCK>();
           float2 cur[8], y[8];
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {

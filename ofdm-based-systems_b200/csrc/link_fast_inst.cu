@@ -80,20 +80,17 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
     return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, true>(L, p, stream)
                 : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, true>(L, p, stream);
   }
-  if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
-  if (dump) return launch_fast_kernel<E, T, true, false>(L, p, stream);
+  if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT>(L, p, stream)
+                          : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT>(L, p, stream);
+  if (dump) return launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT>(L, p, stream);
   // One-warp teams: the warps that share a scheduler walk the code in step (named barrier per scheduler, SYNC = 2;
   // free-running warps lose ~3 % to instruction-cache misses at N = 1024, profiles/).  Multi-warp teams already meet
-  // at their team barriers and lose ~5 % to the extra one (N = 4096), so they run with SYNC = 0.
+  // at their team barriers and lose ~5 % to an extra one (N = 4096), so they run with SYNC = 0.
   // OFDM_B200_FAST_VARIANT=4 / =2 force SYNC = 0 / 2 for experiments.
   static const int variant = [] { const char* v = std::getenv("OFDM_B200_FAST_VARIANT"); return v ? std::atoi(v) : 0; }();
-  const bool free_running = variant == 4 || (variant != 2 && variant != 1 && T > 32);
-  if (free_running) return launch_fast_kernel<E, T, false, false, 512, 0>(L, p, stream);
-  if (variant == 1) return launch_fast_kernel<E, T, false, false, 512, 1>(L, p, stream);
-#if OFDM_FAST_T == 32
-  if (variant == 5) return launch_fast_kernel<E, T, false, false, 512, 4>(L, p, stream);
-#endif
-  return launch_fast_kernel<E, T, false, false>(L, p, stream);
+  const int sync = variant == 4 ? 0 : variant == 2 ? 2 : SYNC_DEFAULT;
+  return sync == 0 ? launch_fast_kernel<E, T, false, false, 512, 0>(L, p, stream)
+                   : launch_fast_kernel<E, T, false, false, 512, 2>(L, p, stream);
 }
 
 }  // namespace ofdm
