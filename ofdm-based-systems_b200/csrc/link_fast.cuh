@@ -164,8 +164,11 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 }
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
-          bool FRAMES = false, int NROUNDS = 10, int FIR_UNROLL = 2>
+          bool FRAMES = false, bool SC = false, int NROUNDS = 10, int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+  // SC: single-carrier OFDM (modulation/models.py:58-91) - the constellation symbols are the time samples; the
+  // receiver runs FFT -> equaliser -> IFFT, i.e. the shared transform body serves phases 1 and 2 instead of 0 and 1
+  static_assert(!SC || (!ADAPT && !FRAMES), "SC-OFDM: one order on every sample, single link");
   static_assert(!(ADAPT && REPLAY), "recorded streams with per-subcarrier orders run on the general kernel");
   static_assert(!FRAMES || (ADAPT && !DUMP && !REPLAY), "frame batches: fused mode with per-frame tables");
   using G = FastGeometry<E, T, BLOCK>;
@@ -309,8 +312,42 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1..4 of each byte
     float2 v[E];
 
+    // ---- transmitter epilogue: PAPR statistics of the time samples x[t + T m] = sample(m) and their publication
+    //      in shared memory for the FIR (prefix/models.py:34-44, simulation/models.py:519-524)
+    auto tx_epilogue = [&](auto&& sample) {
+        float ssum[4] = {0.f, 0.f, 0.f, 0.f}, smax[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains: latency, not issue
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float2 x = sample(m);
+          if constexpr (PAPR) {
+            const float pw = fmaf(x.x, x.x, x.y * x.y);
+            // the cyclic prefix repeats the last P samples; for P <= T: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
+            ssum[m & 3] += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
+            smax[m & 3] = fmaxf(smax[m & 3], pw);
+          }
+          col[W * RS * m] = x;
+        }
+        if (PAPR && P > T) {
+          // long prefix (more than one row of samples): the rows above the last one that it also repeats; rolled
+          // loop over this lane's own samples in shared memory (rare shape, keeps the instruction stream small)
+          const int pm = (N - P) / T, pt = (N - P) % T;
 #pragma unroll 1
-    for (int phase = 0; phase < 2; ++phase) {
+          for (int m = pm; m < E - 1; ++m) {
+            const float2 o = col[W * RS * m];
+            if (m > pm || t >= pt) ssum[0] += fmaf(o.x, o.x, o.y * o.y);
+          }
+        }
+        if (PAPR && active) {
+          acc_pow += double((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));
+          acc_max = fmaxf(acc_max, fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3])));
+        }
+        tsync();
+    };
+
+    // OFDM: rolled, ONE copy of the transform body serves both phases (instruction cache).  SC-OFDM: unrolled, so
+    // that the hand-over of the equalised spectrum in registers between phases 1 and 2 has exact live ranges.
+#pragma unroll(SC ? 3 : 1)
+    for (int phase = 0; phase < (SC ? 3 : 2); ++phase) {
       section_sync<SYNC, BLOCK>();
       if (phase == 0) {
         // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
@@ -377,7 +414,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             v[m] = make_float2(lq, li);
           }
         }
-      } else {
+      } else if (!SC || phase == 1) {
         // ---- channel + noise, in place in shared memory, 8 samples per iteration
         //      (channel/models.py:52-55 restricted to P >= L-1 -> circular; noise/models.py:19-22)
         float2 prev[8];
@@ -466,6 +503,17 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 
       // ---- forward FFT of N = E*T points: radix-E in registers, row/column exchange, twiddle, radix-E; when the
       //      team is wider than E a second exchange and a radix-W pass follow (Stockham: natural order throughout)
+      float2 u[E];
+      // element t + T m of the transform: u[oidx(m)]
+      auto oidx = [](int m) constexpr { return W > 1 ? m : fft_out_index<E>(m); };
+      if constexpr (SC) {
+        if (phase == 0) {
+          // no transform at the single-carrier transmitter: the levels are the time samples
+          tx_epilogue([&](int m) { return make_float2(v[m].y, v[m].x); });
+          continue;
+        }
+      }
+      {
       fft_dit_inplace<E, -1>(v);
 #pragma unroll
       for (int r = 0; r < E; r += 2) {
@@ -473,7 +521,6 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         *reinterpret_cast<float4*>(row + r) = make_float4(a.x, a.y, b.x, b.y);
       }
       tsync();
-      float2 u[E];
 #pragma unroll
       for (int m = 0; m < E; ++m) u[m] = col[W * RS * m];
       tsync();
@@ -511,51 +558,20 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           }
         }
       }
-      // element t + T m of the transform: u[oidx(m)]
-      auto oidx = [](int m) constexpr { return W > 1 ? m : fft_out_index<E>(m); };
+      }
 
       if (phase == 0) {
-        // ---- x~[t + T m] = swap(u[brev m]); PAPR statistics; publish for the FIR (prefix/models.py:34-44)
-        float ssum[4] = {0.f, 0.f, 0.f, 0.f}, smax[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains: latency, not issue
-#pragma unroll
-        for (int m = 0; m < E; ++m) {
-          const float2 o = u[oidx(m)];
-          const float2 x = make_float2(o.y, o.x);
-          if constexpr (PAPR) {
-            const float pw = fmaf(x.x, x.x, x.y * x.y);
-            // the cyclic prefix repeats the last P samples; for P <= T: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
-            ssum[m & 3] += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
-            smax[m & 3] = fmaxf(smax[m & 3], pw);
-          }
-          col[W * RS * m] = x;
-        }
-        if (PAPR && P > T) {
-          // long prefix (more than one row of samples): the rows above the last one that it also repeats; rolled
-          // loop over this lane's own samples in shared memory (rare shape, keeps the instruction stream small)
-          const int pm = (N - P) / T, pt = (N - P) % T;
-#pragma unroll 1
-          for (int m = pm; m < E - 1; ++m) {
-            const float2 o = col[W * RS * m];
-            if (m > pm || t >= pt) ssum[0] += fmaf(o.x, o.x, o.y * o.y);
-          }
-        }
-        if (PAPR && active) {
-          acc_pow += double((ssum[0] + ssum[1]) + (ssum[2] + ssum[3]));
-          acc_max = fmaxf(acc_max, fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3])));
-        }
-        tsync();
-      } else {
-        // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
-        //      simulation/models.py:597-606)
-        // per-symbol MMSE noise estimate; branch-free (mmse_c = 0 for ZF / none) so that the shuffle latency
-        // overlaps the per-subcarrier products below
+        // ---- x~[t + T m] = swap(u[brev m])
+        tx_epilogue([&](int m) { const float2 o = u[oidx(m)]; return make_float2(o.y, o.x); });
+      } else if (SC && phase == 1) {
+        // ---- SC-OFDM: equalise in the frequency domain and hand swap(Z) to the inverse transform of phase 2
         float sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
         float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
 #pragma unroll
         for (int off = (T < 32 ? T : 32) / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-        if constexpr (T > 32) {   // the team spans T / 32 warps
+        if constexpr (T > 32) {
           if (lane == 0) s_red[t / 32] = ss;
           tsync();
           ss = 0.f;
@@ -563,9 +579,6 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           for (int i = 0; i < T / 32; ++i) ss += s_red[i];
         }
         const float sigma2 = ss * mmse_c;
-        unsigned rxc[WORDS], rxr[WORDS];
-#pragma unroll
-        for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           const float2 yv = u[oidx(m)];
@@ -576,6 +589,45 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const float inv = fast_rcp(e.z + sigma2);
           if constexpr (DUMP) {
             if (active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
+          }
+          v[m] = make_float2(-b * inv, a * inv);          // swap(Z~): the forward transform then computes the inverse
+        }
+      } else {
+        // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
+        //      simulation/models.py:597-606)
+        // per-symbol MMSE noise estimate; branch-free (mmse_c = 0 for ZF / none) so that the shuffle latency
+        // overlaps the per-subcarrier products below
+        float sigma2 = 0.f;
+        if constexpr (!SC) {
+          float sq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
+          float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
+#pragma unroll
+          for (int off = (T < 32 ? T : 32) / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+          if constexpr (T > 32) {   // the team spans T / 32 warps
+            if (lane == 0) s_red[t / 32] = ss;
+            tsync();
+            ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < T / 32; ++i) ss += s_red[i];
+          }
+          sigma2 = ss * mmse_c;
+        }
+        unsigned rxc[WORDS], rxr[WORDS];
+#pragma unroll
+        for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float2 yv = u[oidx(m)];
+          const int k = t + T * m;
+          const float4 e = s_eq[k];
+          // SC: yv = swap(z~) of time sample k, already equalised and scaled for the slicer
+          const float a = SC ? yv.y : fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
+          const float b = SC ? -yv.x : fmaf(yv.x, e.y, -yv.y * e.x);  // -Im(Y conj A)
+          const float inv = SC ? 1.0f : fast_rcp(e.z + sigma2);
+          if constexpr (DUMP) {
+            if (!SC && active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
             // 2 (s_k - 1) / knorm_k with knorm_k^2 = 2 (M_k - 1) / 3, M_k = (top + 1)^2
             const float zu = ADAPT ? 2.f * e.w * rsqrtf(fmaxf((e.w * e.w + 2.f * e.w) * (2.f / 3.f), 1e-30f)) : p.z_unscale;
             if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);

@@ -72,6 +72,12 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 
+bool uniform_orders(const int32_t* orders, int n) {
+  for (int k = 1; k < n; ++k)
+    if (orders[k] != orders[0]) return false;
+  return orders[0] >= 4;
+}
+
 int configure(ofdm_link* L) {
   switch (L->d.n_subcarriers) {
 #define X(n) case n: return configure_kernel<n>(L);
@@ -164,7 +170,7 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
              : L->mean_h2 == 0.0            ? INFINITY
                                             : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
   f.slice_top = float(side - 1);
-  const double tap_scale = 1.0 / (L->knorm * std::sqrt((double)N));
+  const double tap_scale = L->d.modulator == OFDM_MOD_SC_OFDM ? 1.0 / L->knorm : 1.0 / (L->knorm * std::sqrt((double)N));
   f.tx_scale2 = (float)(tap_scale * tap_scale);
   f.z_unscale = (float)(2.0 * (side - 1) / L->knorm);
   f.y_scale = (float)(1.0 / std::sqrt((double)N));
@@ -371,7 +377,8 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
       loadable = loadable && (M == 0 || M == 1 || M == 4 || M == 16 || M == 64 || M == 256);
     }
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
-    const bool shape_ok = desc->scheme == OFDM_SCHEME_QAM && desc->modulator == OFDM_MOD_OFDM &&
+    const bool single_carrier = desc->modulator == OFDM_MOD_SC_OFDM;   // one order, no loading tables
+    const bool shape_ok = desc->scheme == OFDM_SCHEME_QAM && (!single_carrier || (uniform_orders(orders, N) && !amp && !rx_gain)) &&
                           desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 && Lt <= kFastTaps && fast_supports_n(N) &&
                           P < N && !(force && force[0] == '1');
     L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
@@ -381,7 +388,9 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
       // levels are 2c-(s-1) = knorm * point and the IFFT is unnormalised: with one order the taps absorb
       // 1/(knorm sqrt N); with per-subcarrier orders 1/knorm_k is applied at the mapper (level_tab)
       L->knorm = L->fast == 1 ? std::sqrt(2.0 * (orders[0] - 1) / 3.0) : 1.0;
-      const double tap_scale = 1.0 / (L->knorm * sqn);
+      // SC-OFDM: no transmitter transform, so the taps absorb 1/knorm only and the receiver's two transforms put
+      // 1/N into the decision table
+      const double tap_scale = single_carrier ? 1.0 / L->knorm : 1.0 / (L->knorm * sqn);
       for (int l = 0; l < kFastTaps; ++l)
         L->taps_fast[l] = l < Lt ? make_float2((float)(taps_chan[2 * l] * tap_scale), (float)(taps_chan[2 * l + 1] * tap_scale))
                                  : make_float2(0.f, 0.f);
@@ -402,7 +411,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
           eqf[k] = make_float4(0.f, 0.f, 1.f, 0.f);   // silent subcarrier: decision index 0, no errors counted
         } else {
           // applied power loading: tx amplitude in the level table, receiver gain in the decision-domain table
-          const double dec = knorm_k / (2.0 * sqn * (side - 1)) * (rx_gain ? rx_gain[k] : 1.0);
+          const double dec = knorm_k / (2.0 * (single_carrier ? double(N) : sqn) * (side - 1)) * (rx_gain ? rx_gain[k] : 1.0);
           if (desc->equalizer == OFDM_EQ_NONE) {
             eqf[k] = make_float4((float)dec, 0.f, 1.f, top);
           } else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) {
@@ -518,7 +527,7 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     f.point = point;
     f.sym_begin = first_symbol;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);
@@ -553,7 +562,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
     f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
     f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, true, false, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, true, false, L->d.modulator == OFDM_MOD_SC_OFDM, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);

@@ -1,4 +1,4 @@
-"""Time the fused headline launch with the device-side API: python tools/time_fused.py [N] [order] [symbols] [reps]"""
+"""Time the fused headline launch with the device-side API: python tools/time_fused.py [N] [order] [symbols] [reps] [OFDM|SC-OFDM]"""
 import ctypes, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,9 +8,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 order = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 nsym = int(sys.argv[3]) if len(sys.argv) > 3 else 162761
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+modulator = sys.argv[5] if len(sys.argv) > 5 else "OFDM"
 taps = np.load(os.path.join(ROOT, "config", "channel_models", "severe_multipath.npy"))
 taps = taps / np.sqrt(np.sum(np.abs(taps) ** 2))
-link = nat.Link(n, taps, np.fft.fft(taps, n), np.full(n, order), prefix_type="CYCLIC", prefix_len=7, equalizer="MMSE")
+link = nat.Link(n, taps, np.fft.fft(taps, n), np.full(n, order), prefix_type="CYCLIC", prefix_len=7, equalizer="MMSE", modulator=modulator)
 sigma = float(np.sqrt(1 / 10 ** 2.0 / 2))
 for i in range(3):
     link.run_fused(20.0, sigma, nsym, seed=i)
