@@ -46,6 +46,7 @@ struct FastParams {
   float tx_scale2;          // |tx|^2 = tx_scale2 * |x~|^2 (PAPR statistics)
   float z_unscale;          // DUMP only: Z = (Y~ conj A / (G + sigma2)) * z_unscale   (= 2 (s-1) / k)
   int prefix_len;
+  int zero_prefix;          // 1: zero-padding guard interval (prefix/models.py:60-101), folded by overlap-add; 0: cyclic prefix
   int equalizer;
   int half_bits;            // log2(s)
   unsigned int field_mask;  // (s-1) << 1 replicated in every byte
@@ -156,6 +157,19 @@ __device__ __forceinline__ float2 fast_noise(uint32_t wr, uint32_t wa, uint32_t 
   return make_float2(rad * __cosf(ang), rad * __sinf(ang));
 }
 
+// Zero-padding guard interval, overlap-add at the receiver (prefix/models.py:71-101): the noise of tail sample N + n
+// lands on sample n < P.  `row` holds this lane's samples E t .. E t + E - 1; one Philox call per folded sample.
+template <int E, int NROUNDS>
+__device__ __noinline__ void zero_prefix_tail_noise(float2* row, int t, int P, uint32_t gs_lo, uint32_t gs_hi, uint32_t point,
+                                                    PhiloxKey key, float noise_c2, float2* dump_noise, unsigned long long dump_base) {
+  for (int n = E * t; n < P && n < E * t + E; ++n) {
+    const uint4 w = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (2u << 28) | (uint32_t)n, point), key);
+    const float2 g = fast_noise(w.x, w.y, 0x7610u, noise_c2);
+    if (dump_noise) dump_noise[dump_base + n] = g;
+    row[n - E * t] = cadd(row[n - E * t], g);
+  }
+}
+
 // prefix-XOR inside the 4-bit fields that sit at bits 1..4 of every byte (inverse Gray code)
 __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   x ^= x >> 1;
@@ -199,6 +213,10 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 
   const PhiloxKey key{(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
   const int P = p.prefix_len;
+  // With a guard interval at least as long as the channel memory, a zero-padded symbol folded by overlap-add sees the
+  // same circular convolution as a cyclic-prefixed one.  What differs: no prefix power in the PAPR statistics (Pc = 0),
+  // the noise of the P folded tail samples adds to the first P samples, and the stream index of sample n is n, not P + n.
+  const int Pc = p.zero_prefix ? 0 : P, noise_off = p.zero_prefix ? 0 : P;
   const float magic = 8388608.0f;  // 2^23
   // symbols of this pass: s = s_lo + it * s_stride + s_first < s_hi, global index sym_base + s.  One pass over the
   // launch's range, or (FRAMES) one pass per (frame, chunk) unit with the whole block on the same frame.
@@ -322,15 +340,15 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           if constexpr (PAPR) {
             const float pw = fmaf(x.x, x.x, x.y * x.y);
             // the cyclic prefix repeats the last P samples; for P <= T: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
-            ssum[m & 3] += (m == E - 1 && t >= T - P) ? 2.f * pw : pw;
+            ssum[m & 3] += (m == E - 1 && t >= T - Pc) ? 2.f * pw : pw;
             smax[m & 3] = fmaxf(smax[m & 3], pw);
           }
           col[W * RS * m] = x;
         }
-        if (PAPR && P > T) {
+        if (PAPR && Pc > T) {
           // long prefix (more than one row of samples): the rows above the last one that it also repeats; rolled
           // loop over this lane's own samples in shared memory (rare shape, keeps the instruction stream small)
-          const int pm = (N - P) / T, pt = (N - P) % T;
+          const int pm = (N - Pc) / T, pt = (N - Pc) % T;
 #pragma unroll 1
           for (int m = pm; m < E - 1; ++m) {
             const float2 o = col[W * RS * m];
@@ -465,7 +483,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
               for (int i = 0; i < 8; ++i) {
                 const float2 g = fast_noise(rw[i], aw[i >> 1], (i & 1) ? 0x7632u : 0x7610u, noise_c2);
                 if constexpr (DUMP) {
-                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + P + E * t + 8 * c + i] = g;
+                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
                 }
                 y[i] = cadd(y[i], g);
               }
@@ -477,13 +495,18 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
           for (int i = 0; i < 8; ++i) prev[i] = cur[i];
         }
+        if constexpr (!REPLAY) {
+          if (p.zero_prefix)   // rare link shape: kept out of line so that the hot instruction stream stays small
+            zero_prefix_tail_noise<E, NROUNDS>(row, t, P, gs_lo, gs_hi, p.point, key, noise_c2,
+                                               (DUMP && active) ? p.dump_noise : nullptr, s * (unsigned long long)(N + P) + N);
+        }
         tsync();
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = col[W * RS * m];
         if constexpr (REPLAY) {
           // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples (the lines
           // were pulled into L2 one OFDM symbol ago)
-          const unsigned long long ni = (active ? s : 0ull) * (unsigned long long)(N + P) + P + t;
+          const unsigned long long ni = (active ? s : 0ull) * (unsigned long long)(N + P) + noise_off + t;
           if (p.noise && !p.noise_f64) {
             const float2* nz = reinterpret_cast<const float2*>(p.noise) + ni;
 #pragma unroll
@@ -494,6 +517,23 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             for (int m = 0; m < E; ++m) {
               const double2 g = __ldg(nz + T * m);
               v[m] = cadd(v[m], make_float2((float)g.x, (float)g.y));
+            }
+          }
+          if (p.zero_prefix && p.noise) {
+            // overlap-add of the recorded tail noise: stream sample N + n onto sample n = t + T m < P
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+              if (t + T * m < P) {
+                const unsigned long long ti = ni + N + T * m;
+                float2 g;
+                if (p.noise_f64) {
+                  const double2 d = __ldg(reinterpret_cast<const double2*>(p.noise) + ti);
+                  g = make_float2((float)d.x, (float)d.y);
+                } else {
+                  g = __ldg(reinterpret_cast<const float2*>(p.noise) + ti);
+                }
+                v[m] = cadd(v[m], g);
+              }
             }
           }
         }

@@ -175,6 +175,7 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   f.z_unscale = (float)(2.0 * (side - 1) / L->knorm);
   f.y_scale = (float)(1.0 / std::sqrt((double)N));
   f.prefix_len = L->d.prefix_len;
+  f.zero_prefix = L->d.prefix_type == OFDM_PREFIX_ZERO;
   f.equalizer = L->d.equalizer;
   f.half_bits = half_bits;
   f.field_mask = 0x01010101u * (unsigned)((side - 1) << 1);
@@ -379,7 +380,8 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
     const bool single_carrier = desc->modulator == OFDM_MOD_SC_OFDM;   // one order, no loading tables
     const bool shape_ok = desc->scheme == OFDM_SCHEME_QAM && (!single_carrier || (uniform_orders(orders, N) && !amp && !rx_gain)) &&
-                          desc->prefix_type == OFDM_PREFIX_CYCLIC && P >= Lt - 1 && Lt <= kFastTaps && fast_supports_n(N) &&
+                          (desc->prefix_type == OFDM_PREFIX_CYCLIC || desc->prefix_type == OFDM_PREFIX_ZERO) && P >= Lt - 1 &&
+                          Lt <= kFastTaps && fast_supports_n(N) &&
                           P < N && !(force && force[0] == '1');
     L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
     if (L->fast) {
