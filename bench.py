@@ -286,7 +286,7 @@ def run_b200_arm(args) -> None:
             from bench_replay import measure as replay_measure
             rp = replay_measure(symbols=100_000, reps=5)
             line["replay"] = {"value": rp["bits_per_s"], "unit": "bits/s", "achieved_gbs": rp["achieved_gbs"],
-                              "hbm_peak_gbs": rp["hbm_peak_gbs"], "frac_hbm": rp["frac_hbm"],
+                              "hbm_peak_gbs": rp["hbm_peak_gbs"], "hbm_peak_source": rp["hbm_peak_source"], "frac_hbm": rp["frac_hbm"],
                               "algorithmic_bytes_per_symbol": rp["algorithmic_bytes_per_symbol"],
                               "algorithmic_tflops": rp["algorithmic_tflops"], "symbols_per_launch": rp["symbols"],
                               "what": "ofdm_link_launch_replay: recorded bits (768 B) + complex64 noise (8 248 B) per OFDM "
