@@ -175,3 +175,45 @@ def test_device_side_sweep_equals_synchronous_sweep(kat):
             assert x[key] == y[key]
         assert abs(x["papr_db"] - y["papr_db"]) < 1e-9
     sweep.close()
+
+
+def test_qpsk_awgn_curve_matches_theory(kat):
+    """BASELINE config #1 shape (N=64, QPSK, CP=16, one-tap channel, ZF): BER(SNR) = Q(sqrt(SNR)) - the analytic anchor
+    SURVEY 6 reproduced with the reference (0.1587 at 0 dB, 7.8e-4 at 10 dB)."""
+    from scipy.stats import norm
+    from ofdm_based_systems.simulation.sweep import LinkConfig, LinkSweep
+    cfg = LinkConfig(num_subcarriers=64, taps_raw=kat["chan_flat_fading"], constellation_order=4, prefix_length=16,
+                     equalizator_type="ZF")
+    snrs = [0.0, 2.0, 4.0, 6.0, 8.0, 10.0, 12.0]
+    sweep = LinkSweep(cfg)
+    res = sweep.sweep(snrs, 1_000_000, seed=31)                    # 1.28e8 bits per point
+    sweep.close()
+    for snr, r in zip(snrs, res):
+        theory = norm.sf(np.sqrt(10 ** (snr / 10)))
+        sem = np.sqrt(theory * (1 - theory) / r["total_bits"])
+        assert abs(r["bit_error_rate"] - theory) < 5 * sem + 1e-9, (snr, r["bit_error_rate"], theory)
+
+
+def test_headline_ber_curve_inside_reference_confidence_intervals(kat):
+    """north_star: independent-RNG BER curves must lie inside the reference's 95 % confidence intervals.  Reference side:
+    the oracle with NumPy's generators, per-OFDM-symbol error counts -> standard error; 8 SNR points of the headline
+    link.  The band used is +-3.3 s.e. per point so that the 8-point family stays at ~95 %."""
+    from ofdm_based_systems.simulation.sweep import LinkConfig, LinkSweep
+    n, order, P, bps, n_ofdm = 1024, 64, 7, 6, 60
+    taps = kat["chan_severe_multipath"]
+    snrs = [0.0, 4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0]
+    cfg = LinkConfig(num_subcarriers=n, taps_raw=taps, constellation_order=order, prefix_length=P, equalizator_type="MMSE")
+    sweep = LinkSweep(cfg)
+    got = sweep.sweep(snrs, 20_000, seed=123)
+    sweep.close()
+    rng = np.random.default_rng(77)
+    for snr, g in zip(snrs, got):
+        setup = oc.LinkSetup(n_sc=n, taps_raw=taps, snr_db=snr, order=order, eq="MMSE", prefix_len_override=P)
+        tx = oc.generate_bits(n_ofdm * n * bps, rng)
+        shape = (n_ofdm * (n + P),)
+        ref = oc.run_link(setup, tx, n_ofdm * n * bps, normals=(rng.normal(size=shape), rng.normal(size=shape)))
+        tb = oc.unpack_bits(tx).reshape(n_ofdm, n * bps)
+        rb = oc.unpack_bits(ref["rx_bytes"]).reshape(n_ofdm, n * bps)
+        per_symbol = np.sum(tb != rb, axis=1) / (n * bps)
+        sem = per_symbol.std(ddof=1) / np.sqrt(n_ofdm)
+        assert abs(g["bit_error_rate"] - per_symbol.mean()) <= 3.3 * sem + 1e-12, (snr, g["bit_error_rate"], per_symbol.mean(), sem)
