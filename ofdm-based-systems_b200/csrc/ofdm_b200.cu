@@ -325,7 +325,16 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
   DeviceGuard guard(dev);
 
-  ofdm_link* L = new ofdm_link();
+  // owns the link (and its arena) until the last step succeeded
+  struct LinkOwner {
+    ofdm_link* L;
+    ~LinkOwner() {
+      if (!L) return;
+      g_arenas.release(L->arena, L->table_bytes, L->device);
+      delete L;
+    }
+  } owner{new ofdm_link()};
+  ofdm_link* L = owner.L;
   L->d = *desc;
   L->device = dev;
   // consecutive OFDM symbols interact when the prefix is shorter than the channel memory
@@ -340,10 +349,10 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   for (int k = 0; k < N; ++k) {
     const int M = orders[k];
     int bps = 0;
-    if (M < 0 || (M & (M - 1)) || M > 65536) { delete L; return fail(OFDM_EINVAL, "orders[%d]=%d is not a power of two", k, M); }
+    if (M < 0 || (M & (M - 1)) || M > 65536) return fail(OFDM_EINVAL, "orders[%d]=%d is not a power of two", k, M);
     while ((1 << bps) < M) ++bps;
     if (M <= 1) bps = 0;
-    if (desc->scheme == OFDM_SCHEME_QAM && (bps & 1)) { delete L; return fail(OFDM_EINVAL, "orders[%d]=%d: QAM order must be a perfect square", k, M); }
+    if (desc->scheme == OFDM_SCHEME_QAM && (bps & 1)) return fail(OFDM_EINVAL, "orders[%d]=%d: QAM order must be a perfect square", k, M);
     const double knorm = desc->scheme == OFDM_SCHEME_QAM && M > 1 ? std::sqrt(2.0 * (M - 1) / 3.0) : 1.0;
     const double a = (amp ? amp[k] : 1.0);
     const unsigned info = (unsigned)bps | ((unsigned)bit_off << 8);
@@ -444,7 +453,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   }
 
   int rc = configure(L);
-  if (rc != OFDM_OK) { delete L; return rc; }
+  if (rc != OFDM_OK) return rc;
   CUDA_TRY(cudaDeviceGetAttribute(&L->sms, cudaDevAttrMultiProcessorCount, dev));
 
   // one device arena, one host->device copy: [counters | sc | eq | eq_fast | twiddles]
@@ -462,8 +471,9 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   if (!level_host.empty()) std::memcpy(stage.data() + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
   if (!mask_host.empty()) std::memcpy(stage.data() + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
   unsigned char* arena = g_arenas.acquire(total, dev);
-  if (!arena) { delete L; cudaGetLastError(); return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of link tables) failed", total); }
+  if (!arena) { cudaGetLastError(); return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of link tables) failed", total); }
   L->arena = arena;
+  L->table_bytes = total;
   CUDA_TRY(cudaMemcpy(arena, stage.data(), total, cudaMemcpyHostToDevice));
   L->d_cnt = reinterpret_cast<CounterBlock*>(arena);
   L->d_sc = reinterpret_cast<float4*>(arena + off_sc);
@@ -473,7 +483,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   L->d_tw_fast = tw_fast_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_twf);
   L->d_level = level_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_lvl);
   L->d_mask = mask_host.empty() ? nullptr : reinterpret_cast<unsigned*>(arena + off_msk);
-  L->table_bytes = total;
+  owner.L = nullptr;
   *out = L;
   return OFDM_OK;
 }
