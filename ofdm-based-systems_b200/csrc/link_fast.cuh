@@ -95,8 +95,9 @@ struct FastGeometry {
   static constexpr int TW3_F2 = W > 1 ? N / W : 0;
   static constexpr int TW_F2 = TW2_F2 + TW3_F2;
   static constexpr int RED_F = T > 32 ? TEAMS * (T / 32) : 0;   // cross-warp reduction scratch (floats)
-  static constexpr size_t SMEM_BYTES =
-      (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) + RED_F * sizeof(float);
+  static constexpr int TAIL_F2 = 8;           // ISI: last tx samples of the previous OFDM symbol, per team
+  static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) +
+                                       RED_F * sizeof(float) + size_t(TEAMS) * TAIL_F2 * sizeof(float2);
 };
 
 // barrier among the lanes of one team: the warp when the team fits one, else a named barrier (ids 5..12)
@@ -178,8 +179,13 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 }
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
-          bool FRAMES = false, bool SC = false, int NROUNDS = 10, int FIR_UNROLL = 2>
+          bool FRAMES = false, bool SC = false, bool ISI = false, int NROUNDS = 10, int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+  // ISI: cyclic prefix shorter than the channel memory, or no prefix (channel/models.py:52-55 over the serial stream):
+  // the FIR reaches into the previous OFDM symbol.  A team then owns a CONTIGUOUS chain of symbols, carries the last 8
+  // tx samples of the previous one in shared memory, and recomputes the transmitter of the symbol before its chain
+  // (one "halo" pass), so the result does not depend on how the symbol range is partitioned.
+  static_assert(!ISI || (!ADAPT && !FRAMES && !SC), "ISI chains: one order, single link, OFDM");
   // SC: single-carrier OFDM (modulation/models.py:58-91) - the constellation symbols are the time samples; the
   // receiver runs FFT -> equaliser -> IFFT, i.e. the shared transform body serves phases 1 and 2 instead of 0 and 1
   static_assert(!SC || (!ADAPT && !FRAMES), "SC-OFDM: one order on every sample, single link");
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   float2* s_tw = smem2 + size_t(G::TEAMS) * G::TEAM_F2;
   float4* s_eq = reinterpret_cast<float4*>(s_tw + G::TW_F2);
   float* s_red = reinterpret_cast<float*>(s_eq + N) + team_in_block * (T / 32);
+  float2* s_tail = reinterpret_cast<float2*>(reinterpret_cast<float*>(s_eq + N) + G::RED_F) + team_in_block * G::TAIL_F2;
   float2* col = buf + trow * RS + tcol;   // strided set: col[W * RS * m]
   auto tsync = [&]() { team_sync<T>(team_in_block); };
 
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
       }
     }
   };
-  replay_prefetch(s_first);
+  if constexpr (!ISI) replay_prefetch(s_first);
 
   auto flush_counters = [&](unsigned long long* counters, double* power_sum, unsigned long long* power_max_bits) {
     // ---- counters: warp shuffle, one atomic per warp
@@ -320,11 +327,25 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     s_first = team_in_block;
     sym_base = p.sym_begin + f * p.frame_syms;
   }
-  const unsigned long long iters = s_hi > s_lo ? (s_hi - s_lo + s_stride - 1) / s_stride : 0;
+  unsigned long long iters = s_hi > s_lo ? (s_hi - s_lo + s_stride - 1) / s_stride : 0;
+  // ISI: contiguous chain [chain_lo, chain_hi) per team, preceded by the halo pass of symbol chain_lo - 1
+  [[maybe_unused]] unsigned long long chain_lo = 0, chain_hi = 0;
+  [[maybe_unused]] bool has_prev = false;
+  if constexpr (ISI) {
+    const unsigned long long per = iters;                 // = ceil(sym_count / teams)
+    chain_lo = s_first * per < s_hi ? s_first * per : s_hi;
+    chain_hi = chain_lo + per < s_hi ? chain_lo + per : s_hi;
+    has_prev = chain_lo < chain_hi && sym_base + chain_lo > 0;
+    iters = per + 1;
+    if (t < G::TAIL_F2) s_tail[t] = make_float2(0.f, 0.f);
+    replay_prefetch(has_prev ? chain_lo - 1 : chain_lo);
+  }
   for (unsigned long long it = 0; it < iters; ++it) {
-    const unsigned long long s = s_lo + it * s_stride + s_first;
-    const bool active = s < s_hi;
-    const unsigned long long gs = sym_base + (active ? s : s_lo);
+    const bool halo = ISI && it == 0;
+    const unsigned long long s = ISI ? (halo ? (has_prev ? chain_lo - 1 : chain_lo) : chain_lo + it - 1)
+                                     : s_lo + it * s_stride + s_first;
+    const bool active = ISI ? (!halo && s < chain_hi) : s < s_hi;
+    const unsigned long long gs = sym_base + ((active || (halo && has_prev)) ? s : s_lo);
     const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
 
     unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1..4 of each byte
@@ -365,7 +386,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     // OFDM: rolled, ONE copy of the transform body serves both phases (instruction cache).  SC-OFDM: unrolled, so
     // that the hand-over of the equalised spectrum in registers between phases 1 and 2 has exact live ranges.
 #pragma unroll(SC ? 3 : 1)
-    for (int phase = 0; phase < (SC ? 3 : 2); ++phase) {
+    for (int phase = 0; phase < (SC ? 3 : (halo ? 1 : 2)); ++phase) {
       section_sync<SYNC, BLOCK>();
       if (phase == 0) {
         // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             if (t + T * j < sym_words) wscr[t + T * j] = __byte_perm(next_bits[j], 0u, 0x0123);
           if (t == 0) wscr[sym_words] = 0u;
           // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
-          replay_prefetch(s + s_stride);
+          replay_prefetch(ISI ? (halo ? chain_lo : s + 1) : s + s_stride);
           tsync();
 #pragma unroll
           for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
@@ -445,7 +466,21 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             prev[i + 1] = make_float2(q.z, q.w);
           }
         }
+        [[maybe_unused]] float2 new_tail;
+        if constexpr (ISI) {
+          // sample -j before the body (j = 8 - i): inside the cyclic prefix for j <= P (the wrap-around above), else
+          // sample N - (j - P) of the previous OFDM symbol
+          if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (8 - i > P) prev[i] = s_tail[i + P];
+          }
+          if (t < G::TAIL_F2) new_tail = buf[(T - 1) * RS + (E - 8) + t];   // this symbol's tail, before the FIR overwrites it
+        }
         tsync();
+        if constexpr (ISI) {
+          if (t < G::TAIL_F2) s_tail[t] = new_tail;   // read again only in the next symbol's channel phase
+        }
 #pragma unroll FIR_UNROLL
         for (int c = 0; c < E / 8; ++c) {
           float2 cur[8], y[8];
@@ -712,6 +747,12 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           acc_sym_err += se;
           acc_syms += E;
         }
+      }
+    }
+    if constexpr (ISI) {
+      if (halo) {   // only the transmitter ran: keep the tail of the symbol before the chain
+        if (has_prev && t < G::TAIL_F2) s_tail[t] = buf[(T - 1) * RS + (E - 8) + t];
+        tsync();
       }
     }
   }

@@ -389,8 +389,12 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
     const char* force = std::getenv("OFDM_B200_FORCE_GENERAL");
     const bool single_carrier = desc->modulator == OFDM_MOD_SC_OFDM;   // one order, no loading tables
     const bool shape_ok = desc->scheme == OFDM_SCHEME_QAM && (!single_carrier || (uniform_orders(orders, N) && !amp && !rx_gain)) &&
-                          (desc->prefix_type == OFDM_PREFIX_CYCLIC || desc->prefix_type == OFDM_PREFIX_ZERO) && P >= Lt - 1 &&
                           Lt <= kFastTaps && fast_supports_n(N) &&
+                          // guard interval at least as long as the channel memory (cyclic or zero-padded), or inter-symbol
+                          // interference with a short cyclic prefix / no prefix: one order, OFDM, chained symbols
+                          ((P >= Lt - 1 && desc->prefix_type != OFDM_PREFIX_NONE) ||
+                           (desc->prefix_type != OFDM_PREFIX_ZERO && !single_carrier && uniform_orders(orders, N) && !amp &&
+                            !rx_gain)) &&
                           P < N && !(force && force[0] == '1');
     L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
     if (L->fast) {
@@ -539,7 +543,7 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     f.point = point;
     f.sym_begin = first_symbol;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);
@@ -574,7 +578,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
     f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
     f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, true, false, L->d.modulator == OFDM_MOD_SC_OFDM, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, true, false, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);

@@ -68,7 +68,7 @@ namespace ofdm {
 struct FastParams;
 bool fast_supports_n(int n);
 int fast_samples_per_lane(int n);
-int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, cudaStream_t stream);
+int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi, cudaStream_t stream);
 }  // namespace ofdm
 
 #define OFDM_FOR_EACH_N(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)

@@ -22,6 +22,7 @@ CASES = [
     ("zp", 256, 16, "QAM", "rayleigh_fading", "ZERO", 5, "MMSE", 15.0, "OFDM", 16),
     ("zp1024", 1024, 64, "QAM", "severe_multipath", "ZERO", 40, "ZF", 26.0, "OFDM", 6),
     ("isi", 128, 64, "QAM", "severe_multipath", "CYCLIC", 2, "ZF", 24.0, "OFDM", 40),
+    ("isi1024", 1024, 16, "QAM", "severe_multipath", "CYCLIC", 3, "MMSE", 19.0, "OFDM", 37),
     ("none", 64, 16, "QAM", "Lin-Phoong_P2", "NONE", 0, "MMSE", 22.0, "OFDM", 48),
     ("sc", 512, 4, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "ZF", 8.0, "SC-OFDM", 10),
     ("sc4096", 4096, 64, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 21.0, "SC-OFDM", 5),
@@ -53,7 +54,7 @@ def test_fused_dump_replays_through_oracle(case, kat):
     sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
     link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
                 modulator=modulator, equalizer=eq, scheme=scheme)
-    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512", "sc", "sc4096", "zp", "zp1024"))
+    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512", "sc", "sc4096", "zp", "zp1024", "isi", "none", "isi1024"))
     # with inter-symbol interference the oracle's stream must start where the kernel's does (zero history)
     first = 0 if len(taps_raw) - 1 > P else 1000
     res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=first,
