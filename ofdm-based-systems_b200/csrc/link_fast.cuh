@@ -70,6 +70,10 @@ struct FastParams {
   const unsigned int* field_masks;   // [(E/4) * T]: word j of lane t = ((s_k - 1) << 1) in byte i for k = t + T (4 j + i)
   const float2* level_tab;           // [N]: {g_k, -(2^23 + s_k)} with g_k = 1 / sqrt(2 (M_k - 1) / 3)  (0 when silent);
                                      // the slicer's s_k - 1 is the 4th component of eq_tab
+  // PSK instantiation (constellation/models.py:356-474): labels of psk_bits bits, one per byte of the packed words
+  const float2* psk_tab;    // [256]: label -> exp(j 2 pi gray^-1(label) / M)
+  int psk_bits;             // log2 M, 1 .. 8
+  float psk_scale;          // M / (2 pi)
   // FRAMES instantiation (always with ADAPT): a batch of channel realisations, `frame_syms` OFDM symbols each.
   // eq_tab / level_tab / field_masks hold one table per frame ([F][N], [F][N], [F][N/4]); a (frame, chunk) unit is
   // processed by one block, which loads the frame's tables into shared memory when the frame changes.
@@ -96,8 +100,9 @@ struct FastGeometry {
   static constexpr int TW_F2 = TW2_F2 + TW3_F2;
   static constexpr int RED_F = T > 32 ? TEAMS * (T / 32) : 0;   // cross-warp reduction scratch (floats)
   static constexpr int TAIL_F2 = 8;           // ISI: last tx samples of the previous OFDM symbol, per team
+  static constexpr int PSK_F2 = 256;          // PSK: point table
   static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) +
-                                       RED_F * sizeof(float) + size_t(TEAMS) * TAIL_F2 * sizeof(float2);
+                                       RED_F * sizeof(float) + (size_t(TEAMS) * TAIL_F2 + PSK_F2) * sizeof(float2);
 };
 
 // barrier among the lanes of one team: the warp when the team fits one, else a named barrier (ids 5..12)
@@ -179,8 +184,11 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 }
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
-          bool FRAMES = false, bool SC = false, bool ISI = false, int NROUNDS = 10, int FIR_UNROLL = 2>
+          bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2>
 __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+  // PSK: M-ary phase-shift keying, one order on every subcarrier; labels through a shared-memory point table at the
+  // transmitter, angle rounding at the receiver (the equaliser's positive real denominator does not move the angle)
+  static_assert(!PSK || (!ADAPT && !FRAMES && !SC && !ISI), "PSK: one order, single link, OFDM, no ISI");
   // ISI: cyclic prefix shorter than the channel memory, or no prefix (channel/models.py:52-55 over the serial stream):
   // the FIR reaches into the previous OFDM symbol.  A team then owns a CONTIGUOUS chain of symbols, carries the last 8
   // tx samples of the previous one in shared memory, and recomputes the transmitter of the symbol before its chain
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   float4* s_eq = reinterpret_cast<float4*>(s_tw + G::TW_F2);
   float* s_red = reinterpret_cast<float*>(s_eq + N) + team_in_block * (T / 32);
   float2* s_tail = reinterpret_cast<float2*>(reinterpret_cast<float*>(s_eq + N) + G::RED_F) + team_in_block * G::TAIL_F2;
+  float2* s_psk = s_tail - team_in_block * G::TAIL_F2 + G::TEAMS * G::TAIL_F2;
   float2* col = buf + trow * RS + tcol;   // strided set: col[W * RS * m]
   auto tsync = [&]() { team_sync<T>(team_in_block); };
 
@@ -215,6 +224,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   for (int i = threadIdx.x; i < G::TW_F2; i += BLOCK) s_tw[i] = __ldg(&p.tw[i]);
   if constexpr (!FRAMES) {
     for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[i]);
+  }
+  if constexpr (PSK) {
+    for (int i = threadIdx.x; i < G::PSK_F2; i += BLOCK) s_psk[i] = __ldg(&p.psk_tab[i]);
   }
   __syncthreads();
 
@@ -243,7 +255,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 
   // ADAPT: this lane's packed field masks; bits per OFDM symbol carried by its E subcarriers
   unsigned fmask[ADAPT ? WORDS : 1];
-  unsigned lane_bits = E * 2 * p.half_bits;
+  unsigned lane_bits = PSK ? E * p.psk_bits : E * 2 * p.half_bits;
   auto load_masks = [&](const unsigned* masks) {
     lane_bits = 0;
 #pragma unroll
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   auto replay_prefetch = [&](unsigned long long sn) {
     if constexpr (REPLAY) {
       if (sn >= p.sym_count) return;
-      const int sym_words = N * 2 * p.half_bits / 32;
+      const int sym_words = N * (PSK ? p.psk_bits : 2 * p.half_bits) / 32;
       const unsigned* src = reinterpret_cast<const unsigned*>(p.bits) + sn * (unsigned long long)sym_words;
 #pragma unroll
       for (int j = 0; j < WORDS; ++j)
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           // the symbol's N*bps/8 bytes -> shared memory as big-endian words (coalesced loads); label k = t + T m is
           // the bps bits at bit offset k*bps, MSB first (constellation/models.py:226-243): a funnel shift over two
           // words.  column = gray(label & (s-1)), row = gray(label >> log2 s); gray is applied on packed words.
-          const int bps = 2 * p.half_bits, sym_words = N * bps / 32;
+          const int bps = PSK ? p.psk_bits : 2 * p.half_bits, sym_words = N * bps / 32;
           unsigned* wscr = reinterpret_cast<unsigned*>(buf);
 #pragma unroll
           for (int j = 0; j < WORDS; ++j)
@@ -412,13 +424,19 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           for (int m = 0; m < E; ++m) {
             const int bit = bit0 + m * tb, w = bit >> 5;
             const unsigned lab = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31) >> (32 - bps);
-            txc[m >> 2] |= (lab & smask) << (8 * (m & 3) + 1);
-            txr[m >> 2] |= (lab >> p.half_bits) << (8 * (m & 3) + 1);
+            if constexpr (PSK) {
+              txc[m >> 2] |= lab << (8 * (m & 3));
+            } else {
+              txc[m >> 2] |= (lab & smask) << (8 * (m & 3) + 1);
+              txr[m >> 2] |= (lab >> p.half_bits) << (8 * (m & 3) + 1);
+            }
           }
+          if constexpr (!PSK) {
 #pragma unroll
-          for (int j = 0; j < WORDS; ++j) {
-            txc[j] = (txc[j] ^ (txc[j] >> 1)) & p.field_mask;
-            txr[j] = (txr[j] ^ (txr[j] >> 1)) & p.field_mask;
+            for (int j = 0; j < WORDS; ++j) {
+              txc[j] = (txc[j] ^ (txc[j] >> 1)) & p.field_mask;
+              txr[j] = (txr[j] ^ (txr[j] >> 1)) & p.field_mask;
+            }
           }
           tsync();
         } else {
@@ -430,8 +448,13 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             for (int j = 0; j < 4; ++j) {
               if (4 * c + j < WORDS) {
                 const unsigned fm = ADAPT ? fmask[ADAPT ? 4 * c + j : 0] : p.field_mask;
-                txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
-                txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
+                if constexpr (PSK) {
+                  txc[4 * c + j] = ww[j] & p.field_mask;   // one label per byte (field_mask = M - 1 in every byte)
+                  txr[4 * c + j] = 0u;
+                } else {
+                  txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
+                  txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
+                }
               }
             }
           }
@@ -439,8 +462,15 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         // level = 2*index - (s-1) as float via the mantissa of 2^23 + (2*index + 1); re/im swapped so the
         // forward FFT below computes the inverse transform
         const float cen = -(magic + p.slice_top + 1.0f);
+        if constexpr (PSK) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
+          for (int m = 0; m < E; ++m) {
+            const float2 pt = s_psk[(txc[m >> 2] >> (8 * (m & 3))) & 0xffu];
+            v[m] = make_float2(pt.y, pt.x);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < (PSK ? 0 : E); ++m) {
           const unsigned fc = __byte_perm(txc[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
           const unsigned fr = __byte_perm(txr[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
           if constexpr (ADAPT) {
@@ -707,6 +737,12 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             const float zu = ADAPT ? 2.f * e.w * rsqrtf(fmaxf((e.w * e.w + 2.f * e.w) * (2.f / 3.f), 1e-30f)) : p.z_unscale;
             if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);
           }
+          if constexpr (PSK) {
+            // nearest point = nearest angle: k = rint(arg(z) M / 2 pi) mod M, label = gray(k)
+            const unsigned kh = (unsigned)__float2int_rn(atan2f(-b, a) * p.psk_scale) & ((1u << p.psk_bits) - 1u);
+            rxc[m >> 2] |= (kh ^ (kh >> 1)) << (8 * (m & 3));
+            continue;
+          }
           // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
           const float top = ADAPT ? e.w : p.slice_top;
           const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
@@ -720,6 +756,25 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         for (int j = 0; j < WORDS; ++j) {
           // sum over the 4 bytes of (0x4B000000 << (8i+1)) mod 2^32: only i = 0 survives
           constexpr unsigned K = (0x4B000000u << 1);
+          if constexpr (PSK) {
+            const unsigned d = rxc[j] ^ txc[j];
+            be += __popc(d);
+            unsigned any = d | (d >> 4);
+            any |= any >> 2;
+            any |= any >> 1;
+            se += __popc(any & 0x01010101u);
+            if constexpr (DUMP) {
+              if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int k = t + T * (4 * j + i);
+                  if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((txc[j] >> (8 * i)) & 0xffu);
+                  if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((rxc[j] >> (8 * i)) & 0xffu);
+                }
+              }
+            }
+            continue;
+          }
           const unsigned dc = ((rxc[j] - K) ^ txc[j]) & 0x1E1E1E1Eu;
           const unsigned dr = ((rxr[j] - K) ^ txr[j]) & 0x1E1E1E1Eu;
           be += __popc(inv_gray_fields(dc) & 0x1E1E1E1Eu) + __popc(inv_gray_fields(dr) & 0x1E1E1E1Eu);

@@ -47,10 +47,10 @@ int launch_frames_shape<OFDM_FAST_E, OFDM_FAST_T>(int sms, const FastParams& p0,
 }
 
 template <int E, int T, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2, bool ADAPT = false, bool SC = false,
-          bool ISI = false>
+          bool ISI = false, bool PSK = false>
 static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
   using G = FastGeometry<E, T, BLOCK>;
-  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT, false, SC, ISI>;
+  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT, false, SC, ISI, PSK>;
   static int occ = 0;   // per process: attribute + occupancy query cost ~0.1 ms each
   if (occ == 0) {
     if (G::SMEM_BYTES > 48 * 1024)
@@ -70,13 +70,20 @@ static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStrea
 
 template <int E, int T>
 int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi,
-                      cudaStream_t stream);
+                      bool psk, cudaStream_t stream);
 
 template <>
 int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
-                                                bool adapt, bool sc, bool isi, cudaStream_t stream) {
+                                                bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream) {
   constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T;
   constexpr int SYNC_DEFAULT = T > 32 ? 0 : 2;
+  if (psk) {  // M-ary PSK, one order
+    if (adapt || sc || isi) return fail(OFDM_EUNSUPPORTED, "this PSK link shape runs on the general kernel");
+    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream)
+                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream);
+    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream);
+  }
   if (isi) {  // prefix shorter than the channel memory: chained symbols
     if (adapt || sc) return fail(OFDM_EUNSUPPORTED, "inter-symbol interference with loading tables or SC-OFDM runs on the general kernel");
     if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, false, true>(L, p, stream)

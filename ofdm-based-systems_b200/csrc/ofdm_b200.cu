@@ -179,6 +179,15 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   f.equalizer = L->d.equalizer;
   f.half_bits = half_bits;
   f.field_mask = 0x01010101u * (unsigned)((side - 1) << 1);
+  if (L->fast == 3) {
+    int bps = 0;
+    while ((1 << bps) < L->fixed_order) ++bps;
+    f.psk_tab = L->d_psk;
+    f.psk_bits = bps;
+    f.psk_scale = (float)(double(L->fixed_order) / (2.0 * M_PI));
+    f.field_mask = 0x01010101u * (unsigned)(L->fixed_order - 1);
+    f.z_unscale = 1.f;
+  }
   f.counters = L->d_cnt->cnt;
   f.tx_power_sum = &L->d_cnt->power_sum;
   f.tx_power_max_bits = &L->d_cnt->power_max_bits;
@@ -377,7 +386,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   // ---- fast-path eligibility (link_fast.cuh) and its folded tables
   //      fast = 1: one QAM order on every subcarrier; fast = 2: per-subcarrier orders (adaptive loading)
   std::vector<float4> eq_fast_host;
-  std::vector<float2> tw_fast_host, level_host;
+  std::vector<float2> tw_fast_host, level_host, psk_host;
   std::vector<unsigned> mask_host;
   {
     bool uniform = true, loadable = true;
@@ -397,9 +406,14 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
                             !rx_gain)) &&
                           P < N && !(force && force[0] == '1');
     L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
+    // PSK: one order M = 2 .. 256 on every subcarrier, OFDM, guard interval at least as long as the channel memory
+    const bool psk_ok = desc->scheme == OFDM_SCHEME_PSK && uniform && orders[0] >= 2 && orders[0] <= 256 && !amp && !rx_gain &&
+                        desc->modulator == OFDM_MOD_OFDM && desc->prefix_type != OFDM_PREFIX_NONE && P >= Lt - 1 && P < N &&
+                        Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1');
+    if (psk_ok) L->fast = 3;
     if (L->fast) {
       const double sqn = std::sqrt((double)N);
-      L->fixed_order = L->fast == 1 ? orders[0] : 0;
+      L->fixed_order = (L->fast == 1 || L->fast == 3) ? orders[0] : 0;
       // levels are 2c-(s-1) = knorm * point and the IFFT is unnormalised: with one order the taps absorb
       // 1/(knorm sqrt N); with per-subcarrier orders 1/knorm_k is applied at the mapper (level_tab)
       L->knorm = L->fast == 1 ? std::sqrt(2.0 * (orders[0] - 1) / 3.0) : 1.0;
@@ -415,7 +429,24 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
       const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
       level_host.assign(N, make_float2(0.f, -8388609.0f));
       mask_host.assign(size_t(E / 4) * T, 0u);
-      for (int k = 0; k < N; ++k) {
+      if (L->fast == 3) {
+        // PSK tables: A = H / sqrt(N) (receiver transform), label -> exp(j 2 pi gray^-1(label) / M)
+        const int M = orders[0];
+        for (int k = 0; k < N; ++k) {
+          const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
+          if (desc->equalizer == OFDM_EQ_NONE) eqf[k] = make_float4((float)(1.0 / sqn), 0.f, 1.f, 0.f);
+          else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) eqf[k] = make_float4((float)(1e10 / sqn), 0.f, 1.f, 0.f);
+          else eqf[k] = make_float4((float)(H.real() / sqn), (float)(H.imag() / sqn), (float)std::norm(H), 0.f);
+        }
+        psk_host.assign(256, make_float2(1.f, 0.f));
+        for (int lab = 0; lab < M; ++lab) {
+          int kk = lab;
+          for (int sh = 1; sh < 8; sh <<= 1) kk ^= kk >> sh;          // inverse Gray code
+          const double ang = 2.0 * M_PI * double(kk) / double(M);
+          psk_host[lab] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+      }
+      for (int k = 0; k < N && L->fast != 3; ++k) {
         const int M = orders[k] < 4 ? 1 : orders[k];
         int side = 1;
         while (side * side < M) side *= 2;
@@ -452,7 +483,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
           const double ang = -2.0 * M_PI * double(j) / double(N);
           tw_fast_host.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
         }
-      if (L->fast == 1) { level_host.clear(); mask_host.clear(); }
+      if (L->fast != 2) { level_host.clear(); mask_host.clear(); }
     }
   }
 
@@ -465,7 +496,8 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   const size_t off_sc = 256, off_eq = off_sc + N * sizeof(float4), off_eqf = off_eq + N * sizeof(float4),
                off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), off_twf = off_tw + tw.size() * sizeof(float2),
                off_lvl = off_twf + tw_fast_host.size() * sizeof(float2), off_msk = off_lvl + level_host.size() * sizeof(float2),
-               total = off_msk + mask_host.size() * sizeof(unsigned);
+               off_psk = (off_msk + mask_host.size() * sizeof(unsigned) + 15) & ~size_t(15),
+               total = off_psk + psk_host.size() * sizeof(float2);
   std::vector<unsigned char> stage(total, 0);
   std::memcpy(stage.data() + off_sc, sc.data(), N * sizeof(float4));
   std::memcpy(stage.data() + off_eq, eq.data(), N * sizeof(float4));
@@ -474,6 +506,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   if (!tw_fast_host.empty()) std::memcpy(stage.data() + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
   if (!level_host.empty()) std::memcpy(stage.data() + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
   if (!mask_host.empty()) std::memcpy(stage.data() + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
+  if (!psk_host.empty()) std::memcpy(stage.data() + off_psk, psk_host.data(), psk_host.size() * sizeof(float2));
   unsigned char* arena = g_arenas.acquire(total, dev);
   if (!arena) { cudaGetLastError(); return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of link tables) failed", total); }
   L->arena = arena;
@@ -487,6 +520,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   L->d_tw_fast = tw_fast_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_twf);
   L->d_level = level_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_lvl);
   L->d_mask = mask_host.empty() ? nullptr : reinterpret_cast<unsigned*>(arena + off_msk);
+  L->d_psk = psk_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_psk);
   owner.L = nullptr;
   *out = L;
   return OFDM_OK;
@@ -543,7 +577,7 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     f.point = point;
     f.sym_begin = first_symbol;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, false, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, L->fast == 3, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);
@@ -568,7 +602,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
   if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
   DeviceGuard guard(L->device);
   const uint64_t whole = n_symbols * (uint64_t)L->bits_per_ofdm;
-  if (L->fast == 1 && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
+  if ((L->fast == 1 || L->fast == 3) && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
       (reinterpret_cast<uintptr_t>(bits_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(noise_dev) & 15) == 0) {
     // common link shape, whole OFDM symbols: the fast kernel streams the recorded bits and noise
     FastParams f;
@@ -578,7 +612,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
     f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
     f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, true, false, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, true, false, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, L->fast == 3, (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);

@@ -48,11 +48,12 @@ struct ofdm_link {
   size_t smem = 0;
   size_t table_bytes = 0;
   // fast path (link_fast.cuh): eligible link shapes only
-  int fast = 0;                 // fast kernel: 0 no, 1 one QAM order on all subcarriers, 2 per-subcarrier orders
+  int fast = 0;                 // fast kernel: 0 no, 1 one QAM order on all subcarriers, 2 per-subcarrier orders / loading, 3 PSK
   int fixed_order = 0;          // the single QAM order when fast
   float4* d_eq_fast = nullptr;  // decision-domain equaliser table
   float2* d_level = nullptr;    // fast = 2: {1/knorm_k, -(2^23 + s_k)}
   unsigned* d_mask = nullptr;   // fast = 2: packed field masks
+  float2* d_psk = nullptr;      // fast = 3: PSK point table [256]
   float2* d_tw_fast = nullptr;  // pass-2 twiddles [(r-1)*E + k], then the pass-3 base twiddles exp(-2 pi i j / N)
   float2 taps_fast[8];
   double knorm = 1.0;
@@ -68,7 +69,7 @@ namespace ofdm {
 struct FastParams;
 bool fast_supports_n(int n);
 int fast_samples_per_lane(int n);
-int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi, cudaStream_t stream);
+int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream);
 }  // namespace ofdm
 
 #define OFDM_FOR_EACH_N(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)

@@ -27,6 +27,8 @@ CASES = [
     ("sc", 512, 4, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "ZF", 8.0, "SC-OFDM", 10),
     ("sc4096", 4096, 64, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", 21.0, "SC-OFDM", 5),
     ("psk", 2048, 8, "PSK", "two_ray", "CYCLIC", 1, "MMSE", 15.0, "OFDM", 4),
+    ("psk64", 256, 64, "PSK", "rayleigh_fading", "ZERO", 6, "ZF", 30.0, "OFDM", 16),
+    ("bpsk", 64, 2, "PSK", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", 4.0, "OFDM", 64),
     ("n8192", 8192, 16, "QAM", "default_multipath", "CYCLIC", 3, "MMSE", 18.0, "OFDM", 2),
     ("n16", 16, 4, "QAM", "two_ray", "CYCLIC", 1, "ZF", 10.0, "OFDM", 200),
     ("n32", 32, 16, "QAM", "two_ray", "ZERO", 1, "MMSE", 18.0, "OFDM", 100),
@@ -54,7 +56,7 @@ def test_fused_dump_replays_through_oracle(case, kat):
     sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
     link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
                 modulator=modulator, equalizer=eq, scheme=scheme)
-    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512", "sc", "sc4096", "zp", "zp1024", "isi", "none", "isi1024"))
+    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512", "sc", "sc4096", "zp", "zp1024", "isi", "none", "isi1024", "psk", "psk64", "bpsk"))
     # with inter-symbol interference the oracle's stream must start where the kernel's does (zero history)
     first = 0 if len(taps_raw) - 1 > P else 1000
     res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=first,
