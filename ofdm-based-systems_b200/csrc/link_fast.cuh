@@ -1,11 +1,15 @@
-// ofdm_link_fast kernel: the Monte-Carlo hot loop for the common link shape
-//   OFDM modulator, square QAM of one order on every subcarrier (4 .. 256), cyclic prefix at least as long
-//   as the channel memory (no inter-symbol interference) and at most E samples, <= 8 taps, Philox bits and
-//   noise, N = E*T subcarriers: a team of T lanes with E samples per lane.  T = E in {8, 16, 32}
-//   (N = 64, 256, 1024: two-pass transform); T = 2E or 4E (N = 128, 512 inside a warp; N = 2048, 4096 with a team
-//   of 2 or 4 warps): a third radix-2/4 pass follows a second exchange.
+// ofdm_link_fast kernel: the Monte-Carlo hot loop, <= 8 channel taps, N = E*T subcarriers: a team of T lanes with
+//   E samples per lane.  T = E in {8, 16, 32} (N = 64, 256, 1024: two-pass transform); T = 2E or 4E (N = 128, 512
+//   inside a warp; N = 2048, 4096 with a team of 2 or 4 warps): a third radix-2/4 pass follows a second exchange.
+//   The headline instantiation is OFDM, one square-QAM order (4 .. 256), cyclic prefix >= channel memory, Philox bits
+//   and noise; compile-time flags add, each in its own instantiation so that the headline stream stays untouched:
+//     REPLAY  recorded bits and noise streamed from HBM          ADAPT   per-subcarrier orders / applied power loading
+//     FRAMES  batches of channel realisations (with ADAPT)       SC      single-carrier OFDM (FFT -> EQ -> IFFT)
+//     ISI     short / no prefix: chained symbols, carried tail   PSK     M-ary PSK
+//     DUMP    per-symbol Y, Z, labels, noise for the parity tests
+//   and run-time fields cover the zero-padding guard interval and prefixes longer than one row of samples.
 // Same chain and same reference lines as link_kernel.cuh; what differs is the machine mapping:
-//   * a team of E lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers;
+//   * a team of T lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers;
 //   * ONE forward-FFT body serves both transforms (the IFFT runs as an FFT on re/im-swapped data) and the
 //     FIR + AWGN stage is a rolled loop over 8-sample chunks that works in place in shared memory, so the
 //     per-symbol instruction stream stays small; the warps that share a scheduler walk it in step (named
