@@ -93,3 +93,43 @@ def test_full_size_counters_are_additive_and_reproducible(n, order, per_launch):
     ber = [p.bit_errors / p.bits for p in parts]
     assert max(ber) - min(ber) < 6 * np.sqrt(max(ber) / (parts[0].bits / (n * bps))) + 1e-9
     link.close()
+
+
+VARIANTS = [
+    # name, N, order, scheme, channel, prefix, P, eq, modulator, per-subcarrier orders?
+    ("qam", 1024, 64, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", "OFDM", False),
+    ("wide", 4096, 16, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", "OFDM", False),
+    ("narrow", 128, 16, "QAM", "rayleigh_fading", "CYCLIC", 5, "ZF", "OFDM", False),
+    ("zp", 512, 64, "QAM", "severe_multipath", "ZERO", 9, "MMSE", "OFDM", False),
+    ("sc", 2048, 16, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "SC-OFDM", False),
+    ("isi", 256, 16, "QAM", "severe_multipath", "CYCLIC", 2, "MMSE", "OFDM", False),
+    ("isi_wide", 2048, 64, "QAM", "severe_multipath", "NONE", 0, "ZF", "OFDM", False),
+    ("psk", 1024, 8, "PSK", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),
+    ("adaptive", 1024, 0, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", "OFDM", True),
+    ("general", 8192, 16, "QAM", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),
+]
+
+
+@pytest.mark.parametrize("v", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_every_variant_is_deterministic_and_additive(v, kat):
+    """Same seed -> identical counters run to run (a shared-memory race or an uninitialised read would show up here), and
+    the counters of [0, S) equal the sum over a split of the symbol range for every kernel variant."""
+    from ofdm_based_systems._native import Link
+    name, n, order, scheme, chan, prefix, P, eq, modulator, adaptive = v
+    taps = kat["chan_" + chan]
+    tn = oc.normalize_taps(taps)
+    orders = np.random.default_rng(1).choice([0, 4, 16, 64, 256], size=n) if adaptive else np.full(n, order)
+    link = Link(n, tn, np.fft.fft(taps, n), orders, prefix_type=prefix, prefix_len=P, equalizer=eq, modulator=modulator,
+                scheme=scheme)
+    assert link.uses_fast_kernel == (name != "general")
+    S = max(300, 2_000_000 // n)
+    runs = [link.run_fused(16.0, 0.11, S, seed=8, point=1, first_symbol=77) for _ in range(3)]
+    for r in runs[1:]:
+        assert (r.bit_errors, r.symbol_errors, r.bits, r.tx_power_max) == (runs[0].bit_errors, runs[0].symbol_errors,
+                                                                           runs[0].bits, runs[0].tx_power_max)
+    assert 0 < runs[0].bit_errors < runs[0].bits // 3
+    a = link.run_fused(16.0, 0.11, S // 3, seed=8, point=1, first_symbol=77)
+    b = link.run_fused(16.0, 0.11, S - S // 3, seed=8, point=1, first_symbol=77 + S // 3)
+    assert a.bit_errors + b.bit_errors == runs[0].bit_errors and a.symbol_errors + b.symbol_errors == runs[0].symbol_errors
+    assert max(a.tx_power_max, b.tx_power_max) == runs[0].tx_power_max
+    link.close()
