@@ -202,7 +202,7 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
                o_mask = up(o_level + F * N * 8), o_hdr = up(o_mask + F * N), o_cnt = up(o_hdr + F * sizeof(FrameHeader)),
                o_used = up(o_cnt + F * 80), bytes = o_used + (orders_out ? F * N * 4 : 0);
   const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
-  const size_t tw_count = size_t(E - 1) * E + (Wd > 1 ? N / Wd : 0), o_tw = up(bytes);
+  const size_t tw_count = size_t(E) * (E + 2) + (Wd > 1 ? N / Wd : 0), o_tw = up(bytes);
   {
     const int rc_arena = g_arena.reserve(o_tw + tw_count * sizeof(float2), dev);
     if (rc_arena) return rc_arena;
@@ -258,17 +258,7 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
   CUDA_TRY(cudaGetLastError());
 
   // pass-2 / pass-3 twiddles of the fast transform (same table as ofdm_link_create builds)
-  std::vector<float2> tw;
-  for (int r = 1; r < E; ++r)
-    for (int k = 0; k < E; ++k) {
-      const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
-      tw.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
-    }
-  if (Wd > 1)
-    for (int j = 0; j < N / Wd; ++j) {
-      const double ang = -2.0 * M_PI * double(j) / double(N);
-      tw.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
-    }
+  const std::vector<float2> tw = build_fast_twiddles(N);
   float2* d_tw = reinterpret_cast<float2*>(a + o_tw);
   CUDA_TRY(cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
 

@@ -3,6 +3,9 @@
 #include "link_fast.cuh"
 #include "plan.h"
 
+#include <cmath>
+#include <vector>
+
 namespace ofdm {
 
 template <int E, int T>
@@ -22,6 +25,25 @@ int launch_fast_frames(int n_subcarriers, int sms, const FastParams& p, cudaStre
     case 4096: return launch_frames_shape<32, 128>(sms, p, stream);
     default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", n_subcarriers);
   }
+}
+
+// Twiddles of the fast transform: pass 2, exp(-2 pi i k r / E^2) for leg r = 1 .. E-1 of lane column k at
+// [k * (E + 2) + r - 1] (padded rows, read as 128-bit pairs); then for teams wider than E the pass-3 base twiddles
+// exp(-2 pi i j / N), j < N / (T/E).
+std::vector<float2> build_fast_twiddles(int N) {
+  const int E = fast_samples_per_lane(N), T = N / E, W = T / E, RS = E + 2;
+  std::vector<float2> tw(size_t(E) * RS, make_float2(0.f, 0.f));
+  for (int k = 0; k < E; ++k)
+    for (int r = 1; r < E; ++r) {
+      const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
+      tw[size_t(k) * RS + r - 1] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  if (W > 1)
+    for (int j = 0; j < N / W; ++j) {
+      const double ang = -2.0 * M_PI * double(j) / double(N);
+      tw.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
+    }
+  return tw;
 }
 
 bool fast_supports_n(int n) { return n >= 64 && n <= 4096 && (n & (n - 1)) == 0; }

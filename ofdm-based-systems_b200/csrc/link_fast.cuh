@@ -42,8 +42,8 @@ struct FrameHeader {       // per channel realisation (built on the device by fr
 struct FastParams {
   float2 taps[kFastTaps];   // unit-energy taps / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1), IFFT unscaled)
   const float4* eq_tab;     // {Re A, Im A, G, -}: decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1)
-  const float2* tw;         // pass-2 twiddles exp(-2 pi i k r / E^2) at [(r-1)*E + k], then (T > E) the pass-3 base
-                            // twiddles exp(-2 pi i j / N), j < N / (T/E)
+  const float2* tw;         // pass-2 twiddles exp(-2 pi i k r / E^2) at [k*(E+2) + r-1], then (T > E) the pass-3 base
+                            // twiddles exp(-2 pi i j / N), j < N / (T/E)   (build_fast_twiddles, link_fast.cu)
   float sigma;              // per-component noise standard deviation
   float mmse_c;             // MMSE: sigma2 = mmse_c * sum_k |Y~_k|^2 (Y~ = unscaled FFT output); else unused
   float slice_top;          // s-1
@@ -99,7 +99,7 @@ struct FastGeometry {
   static constexpr int TEAM_F2 = T * RS;      // float2 per team: T rows of E samples
   static constexpr int BLOCK = BLOCK_;
   static constexpr int TEAMS = BLOCK / T;
-  static constexpr int TW2_F2 = (E - 1) * E;  // pass-2 twiddles (float2)
+  static constexpr int TW2_F2 = E * RS;       // pass-2 twiddles (float2): one padded row per lane column, read as 128-bit pairs
   static constexpr int TW3_F2 = W > 1 ? N / W : 0;
   static constexpr int TW_F2 = TW2_F2 + TW3_F2;
   static constexpr int RED_F = T > 32 ? TEAMS * (T / 32) : 0;   // cross-warp reduction scratch (floats)
@@ -635,7 +635,11 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
       tsync();
       section_sync<SYNC, BLOCK>();
 #pragma unroll
-      for (int r = 1; r < E; ++r) u[r] = cmul(u[r], s_tw[(r - 1) * E + tcol]);
+      for (int c = 0; c < E - 1; c += 2) {   // twiddles of legs c + 1 and c + 2 in one 128-bit load (row stride RS: conflict-free)
+        const float4 w = *reinterpret_cast<const float4*>(s_tw + tcol * RS + c);
+        u[c + 1] = cmul(u[c + 1], make_float2(w.x, w.y));
+        if (c + 2 < E) u[c + 2] = cmul(u[c + 2], make_float2(w.z, w.w));
+      }
       fft_dit_inplace<E, -1>(u);
       if constexpr (W > 1) {
         // pass-2 output r of butterfly j = t lands at linear index E*E*(t/E) + E*r + (t%E); reload the strided

@@ -471,18 +471,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
         }
       }
       eq_fast_host.swap(eqf);
-      // twiddles of the fast transform (link_fast.cuh): pass 2 exp(-2 pi i k r / E^2) at [(r-1) E + k], then for
-      // teams wider than E the pass-3 base twiddles exp(-2 pi i j / N), j < N / (T/E)
-      for (int r = 1; r < E; ++r)
-        for (int k = 0; k < E; ++k) {
-          const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
-          tw_fast_host.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
-        }
-      if (Wd > 1)
-        for (int j = 0; j < N / Wd; ++j) {
-          const double ang = -2.0 * M_PI * double(j) / double(N);
-          tw_fast_host.push_back(make_float2((float)std::cos(ang), (float)std::sin(ang)));
-        }
+      tw_fast_host = build_fast_twiddles(N);
       if (L->fast != 2) { level_host.clear(); mask_host.clear(); }
     }
   }

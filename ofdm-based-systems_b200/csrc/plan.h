@@ -69,6 +69,10 @@ namespace ofdm {
 struct FastParams;
 bool fast_supports_n(int n);
 int fast_samples_per_lane(int n);
+}  // namespace ofdm
+#include <vector>
+namespace ofdm {
+std::vector<float2> build_fast_twiddles(int n);
 int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream);
 }  // namespace ofdm
 
