@@ -264,9 +264,10 @@ def run_b200_arm(args) -> None:
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": "bits/s", "n_gpus": world, "steps": args.steps,
-            "warmup": w, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "symbols_per_step_per_gpu": S, "bits_per_step": bits_per_step,
+                       "untimed_steps": w, "untimed_steps_why": "max(W, 3) warm-up steps + 500 so that nvidia-smi (100 ms period) samples the clocks under this load",
                        "parallelism": f"symbol-range shards x{world}, one NCCL all-reduce per step" if world > 1 else "1 GPU (no collective)",
                        "l2": "144 MiB (151 MB > 126 MB L2) memset between timed steps, inside the timed region; the kernel's inputs are generated in registers (86 KB of tables read per launch)"},
             "clocks": clocks.summary(),
