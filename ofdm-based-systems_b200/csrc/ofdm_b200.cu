@@ -99,7 +99,7 @@ int launch(const ofdm_link* L, const LinkParams& p, cudaStream_t stream) {
 // Inter-pass twiddles of the Stockham plan in link_kernel.cuh (forward sign):
 //   pass 2 (radix R2, NS = R1):     tw[(r-1)*(N/R2) + j]       = exp(-2 pi i (j mod NS) r / (NS R2))
 //   pass 3 (radix R3, NS = R1*R2):  tw[TW2 + (r-1)*(N/R3) + j] likewise
-std::vector<float2> build_twiddles(int N, int E) {
+std::vector<float2> compute_twiddles(int N, int E) {
   const int R1 = E, rem = N / R1, R2 = rem < E ? rem : E, R3 = rem / R2;
   std::vector<float2> tw;
   auto add_pass = [&](int R, int NS) {
@@ -118,6 +118,20 @@ std::vector<float2> build_twiddles(int N, int E) {
   add_pass(R3, R1 * R2);
   if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
   return tw;
+}
+
+// The twiddle tables depend on the transform size only: computed once per size and process (a link is created per
+// channel realisation / per sweep, and ~2000 sincos per creation were a third of its host cost).
+template <class Build>
+const std::vector<float2>& cached_twiddles(int key, Build&& build) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, std::vector<float2>>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& e : cache)
+    if (e.first == key) return e.second;
+  cache.reserve(64);            // references stay valid: at most 2 tables per supported size
+  cache.emplace_back(key, build());
+  return cache.back().second;
 }
 
 void fill_params(const ofdm_link* L, LinkParams& p, double snr_db) {
@@ -471,7 +485,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
         }
       }
       eq_fast_host.swap(eqf);
-      tw_fast_host = build_fast_twiddles(N);
+      tw_fast_host = cached_twiddles(-N, [&] { return build_fast_twiddles(N); });
       if (L->fast != 2) { level_host.clear(); mask_host.clear(); }
     }
   }
@@ -481,7 +495,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   CUDA_TRY(cudaDeviceGetAttribute(&L->sms, cudaDevAttrMultiProcessorCount, dev));
 
   // one device arena, one host->device copy: [counters | sc | eq | eq_fast | twiddles]
-  const std::vector<float2> tw = build_twiddles(N, L->E);
+  const std::vector<float2>& tw = cached_twiddles(N, [&] { return compute_twiddles(N, L->E); });
   const size_t off_sc = 256, off_eq = off_sc + N * sizeof(float4), off_eqf = off_eq + N * sizeof(float4),
                off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), off_twf = off_tw + tw.size() * sizeof(float2),
                off_lvl = off_twf + tw_fast_host.size() * sizeof(float2), off_msk = off_lvl + level_host.size() * sizeof(float2),
