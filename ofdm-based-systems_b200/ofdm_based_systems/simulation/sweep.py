@@ -55,6 +55,9 @@ class LinkConfig:
         measures (noise/models.py:14).  With unit-power constellations on the active subcarriers the
         in-symbol sample power is (1/N) sum_k a_k |H_k|^2 (H from the normalised taps); a zero-padded
         stream spreads one symbol's energy over N + P samples."""
+        cached = getattr(self, "_stream_power", None)
+        if cached is not None:
+            return cached
         n = self.num_subcarriers
         a = (self.orders > 1).astype(np.float64)
         if self.amp is not None:
@@ -65,6 +68,7 @@ class LinkConfig:
             p = float(np.mean(a) * np.sum(np.abs(self.taps_chan) ** 2))
         if self.prefix_scheme == "ZERO":
             p *= n / (n + self.prefix_length)
+        self._stream_power = p        # the configuration is fixed after construction
         return p
 
     def noise_sigma(self, snr_db: float) -> float:
