@@ -71,6 +71,8 @@ struct FastParams {
   const unsigned char* bits;
   unsigned long long bits_len;
   // ADAPT instantiation (per-subcarrier QAM orders, constellation/adaptive.py:52-201):
+  const unsigned short* bit_offsets; // [N]: bit offset of subcarrier k inside an OFDM symbol (ADAPT + REPLAY)
+  unsigned int bits_per_ofdm;        // sum of the per-subcarrier bits (ADAPT + REPLAY)
   const unsigned int* field_masks;   // [(E/4) * T]: word j of lane t = ((s_k - 1) << 1) in byte i for k = t + T (4 j + i)
   const float2* level_tab;           // [N]: {g_k, -(2^23 + s_k)} with g_k = 1 / sqrt(2 (M_k - 1) / 3)  (0 when silent);
                                      // the slicer's s_k - 1 is the 4th component of eq_tab
@@ -201,7 +203,6 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   // SC: single-carrier OFDM (modulation/models.py:58-91) - the constellation symbols are the time samples; the
   // receiver runs FFT -> equaliser -> IFFT, i.e. the shared transform body serves phases 1 and 2 instead of 0 and 1
   static_assert(!SC || (!ADAPT && !FRAMES), "SC-OFDM: one order on every sample, single link");
-  static_assert(!(ADAPT && REPLAY), "recorded streams with per-subcarrier orders run on the general kernel");
   static_assert(!FRAMES || (ADAPT && !DUMP && !REPLAY), "frame batches: fused mode with per-frame tables");
   using G = FastGeometry<E, T, BLOCK>;
   constexpr int N = G::N, RS = G::RS, WORDS = E / 4, W = G::W;
@@ -270,15 +271,41 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   };
   if constexpr (ADAPT && !FRAMES) load_masks(p.field_masks);
 
-  unsigned next_bits[REPLAY ? WORDS : 1];
+  // recorded bits of the next OFDM symbol, prefetched one symbol ahead: the words [first, first + n_words) that hold its
+  // bits (word-aligned symbols with one order; any bit offset with per-subcarrier orders, hence one spare register)
+  constexpr int PF = REPLAY ? WORDS + (ADAPT ? 1 : 0) : 1;
+  unsigned next_bits[PF];
   auto replay_prefetch = [&](unsigned long long sn) {
     if constexpr (REPLAY) {
       if (sn >= p.sym_count) return;
-      const int sym_words = N * (PSK ? p.psk_bits : 2 * p.half_bits) / 32;
-      const unsigned* src = reinterpret_cast<const unsigned*>(p.bits) + sn * (unsigned long long)sym_words;
+      unsigned long long first;
+      int n_words;
+      if constexpr (ADAPT) {
+        const unsigned long long bit0 = sn * (unsigned long long)p.bits_per_ofdm;
+        first = bit0 >> 5;
+        n_words = (int)(((bit0 & 31) + p.bits_per_ofdm + 31) >> 5);
+      } else {
+        n_words = N * (PSK ? p.psk_bits : 2 * p.half_bits) / 32;
+        first = sn * (unsigned long long)n_words;
+      }
+      const unsigned* src = reinterpret_cast<const unsigned*>(p.bits) + first;
+      const unsigned long long avail = (p.bits_len >> 2) > first ? (p.bits_len >> 2) - first : 0;   // whole words in the stream
 #pragma unroll
-      for (int j = 0; j < WORDS; ++j)
-        if (t + T * j < sym_words) next_bits[j] = __ldg(src + t + T * j);
+      for (int j = 0; j < PF; ++j) {
+        const int w = t + T * j;
+        if (w < n_words) {
+          if ((unsigned long long)w < avail) {
+            next_bits[j] = __ldg(src + w);
+          } else {   // the stream ends inside this word (byte granular)
+            unsigned word = 0;
+            for (int b = 0; b < 4; ++b) {
+              const unsigned long long byte = (first + w) * 4ull + b;
+              if (byte < p.bits_len) word |= (unsigned)__ldg(p.bits + byte) << (8 * b);
+            }
+            next_bits[j] = word;
+          }
+        }
+      }
       if (p.noise) {
         const int nbytes = (p.noise_f64 ? 16 : 8) * (N + P);
         const char* nz = reinterpret_cast<const char*>(p.noise) + sn * (unsigned long long)nbytes;
@@ -411,10 +438,13 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           // the symbol's N*bps/8 bytes -> shared memory as big-endian words (coalesced loads); label k = t + T m is
           // the bps bits at bit offset k*bps, MSB first (constellation/models.py:226-243): a funnel shift over two
           // words.  column = gray(label & (s-1)), row = gray(label >> log2 s); gray is applied on packed words.
-          const int bps = PSK ? p.psk_bits : 2 * p.half_bits, sym_words = N * bps / 32;
+          const int bps = PSK ? p.psk_bits : 2 * p.half_bits;
+          // ADAPT: the symbol starts at any bit of the stream and every subcarrier has its own width and offset
+          const int intra = ADAPT ? (int)((s * (unsigned long long)p.bits_per_ofdm) & 31) : 0;
+          const int sym_words = ADAPT ? (intra + (int)p.bits_per_ofdm + 31) >> 5 : N * bps / 32;
           unsigned* wscr = reinterpret_cast<unsigned*>(buf);
 #pragma unroll
-          for (int j = 0; j < WORDS; ++j)
+          for (int j = 0; j < PF; ++j)
             if (t + T * j < sym_words) wscr[t + T * j] = __byte_perm(next_bits[j], 0u, 0x0123);
           if (t == 0) wscr[sym_words] = 0u;
           // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
@@ -426,6 +456,15 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const int bit0 = t * bps, tb = T * bps;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
+            if constexpr (ADAPT) {
+              const int hb = __popc((fmask[ADAPT ? m >> 2 : 0] >> (8 * (m & 3))) & 0xffu);   // log2 of the side
+              const int bit = intra + (int)__ldg(&p.bit_offsets[t + T * m]), w = bit >> 5;
+              const unsigned win = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31);
+              const unsigned lab = hb ? win >> (32 - 2 * hb) : 0u;
+              txc[m >> 2] |= (lab & ((1u << hb) - 1u)) << (8 * (m & 3) + 1);
+              txr[m >> 2] |= (lab >> hb) << (8 * (m & 3) + 1);
+              continue;
+            }
             const int bit = bit0 + m * tb, w = bit >> 5;
             const unsigned lab = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31) >> (32 - bps);
             if constexpr (PSK) {
@@ -438,8 +477,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           if constexpr (!PSK) {
 #pragma unroll
             for (int j = 0; j < WORDS; ++j) {
-              txc[j] = (txc[j] ^ (txc[j] >> 1)) & p.field_mask;
-              txr[j] = (txr[j] ^ (txr[j] >> 1)) & p.field_mask;
+              const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
+              txc[j] = (txc[j] ^ (txc[j] >> 1)) & fm;
+              txr[j] = (txr[j] ^ (txr[j] >> 1)) & fm;
             }
           }
           tsync();

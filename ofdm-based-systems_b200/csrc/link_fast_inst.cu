@@ -98,8 +98,9 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
     return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, true>(L, p, stream)
                 : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, true>(L, p, stream);
   }
-  if (adapt) {  // per-subcarrier orders (fused mode only)
-    if (replay) return fail(OFDM_EUNSUPPORTED, "replayed streams with per-subcarrier orders run on the general kernel");
+  if (adapt) {  // per-subcarrier orders / applied power loading
+    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, true>(L, p, stream)
+                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, true>(L, p, stream);
     return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, true>(L, p, stream)
                 : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, true>(L, p, stream);
   }

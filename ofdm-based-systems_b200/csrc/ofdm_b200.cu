@@ -177,6 +177,8 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   f.eq_tab = L->d_eq_fast;
   f.tw = L->d_tw_fast;
   f.field_masks = L->d_mask;
+  f.bit_offsets = L->d_bitoff;
+  f.bits_per_ofdm = (unsigned)L->bits_per_ofdm;
   f.level_tab = L->d_level;
   const double snr_lin = std::pow(10.0, snr_db / 10.0);
   // equalization/models.py:43-49 on the unscaled FFT output Y~ = sqrt(N) Y
@@ -402,6 +404,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   std::vector<float4> eq_fast_host;
   std::vector<float2> tw_fast_host, level_host, psk_host;
   std::vector<unsigned> mask_host;
+  std::vector<unsigned short> bitoff_host;
   {
     bool uniform = true, loadable = true;
     for (int k = 0; k < N; ++k) {
@@ -443,6 +446,16 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
       const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
       level_host.assign(N, make_float2(0.f, -8388609.0f));
       mask_host.assign(size_t(E / 4) * T, 0u);
+      bitoff_host.assign(N, 0);
+      {
+        unsigned off = 0;   // constellation/adaptive.py:178-198: bps_k bits per subcarrier, subcarrier-minor
+        for (int k = 0; k < N; ++k) {
+          bitoff_host[k] = (unsigned short)off;
+          int b = 0;
+          while ((1 << b) < orders[k]) ++b;
+          off += orders[k] >= 4 ? (unsigned)b : 0u;
+        }
+      }
       if (L->fast == 3) {
         // PSK tables: A = H / sqrt(N) (receiver transform), label -> exp(j 2 pi gray^-1(label) / M)
         const int M = orders[0];
@@ -486,7 +499,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
       }
       eq_fast_host.swap(eqf);
       tw_fast_host = cached_twiddles(-N, [&] { return build_fast_twiddles(N); });
-      if (L->fast != 2) { level_host.clear(); mask_host.clear(); }
+      if (L->fast != 2) { level_host.clear(); mask_host.clear(); bitoff_host.clear(); }
     }
   }
 
@@ -499,7 +512,8 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   const size_t off_sc = 256, off_eq = off_sc + N * sizeof(float4), off_eqf = off_eq + N * sizeof(float4),
                off_tw = off_eqf + eq_fast_host.size() * sizeof(float4), off_twf = off_tw + tw.size() * sizeof(float2),
                off_lvl = off_twf + tw_fast_host.size() * sizeof(float2), off_msk = off_lvl + level_host.size() * sizeof(float2),
-               off_psk = (off_msk + mask_host.size() * sizeof(unsigned) + 15) & ~size_t(15),
+               off_bo = off_msk + mask_host.size() * sizeof(unsigned),
+               off_psk = (off_bo + bitoff_host.size() * sizeof(unsigned short) + 15) & ~size_t(15),
                total = off_psk + psk_host.size() * sizeof(float2);
   std::vector<unsigned char> stage(total, 0);
   std::memcpy(stage.data() + off_sc, sc.data(), N * sizeof(float4));
@@ -509,6 +523,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   if (!tw_fast_host.empty()) std::memcpy(stage.data() + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
   if (!level_host.empty()) std::memcpy(stage.data() + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
   if (!mask_host.empty()) std::memcpy(stage.data() + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
+  if (!bitoff_host.empty()) std::memcpy(stage.data() + off_bo, bitoff_host.data(), bitoff_host.size() * sizeof(unsigned short));
   if (!psk_host.empty()) std::memcpy(stage.data() + off_psk, psk_host.data(), psk_host.size() * sizeof(float2));
   unsigned char* arena = g_arenas.acquire(total, dev);
   if (!arena) { cudaGetLastError(); return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of link tables) failed", total); }
@@ -524,6 +539,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
   L->d_level = level_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_lvl);
   L->d_mask = mask_host.empty() ? nullptr : reinterpret_cast<unsigned*>(arena + off_msk);
   L->d_psk = psk_host.empty() ? nullptr : reinterpret_cast<float2*>(arena + off_psk);
+  L->d_bitoff = bitoff_host.empty() ? nullptr : reinterpret_cast<unsigned short*>(arena + off_bo);
   owner.L = nullptr;
   *out = L;
   return OFDM_OK;
@@ -605,7 +621,7 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
   if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
   DeviceGuard guard(L->device);
   const uint64_t whole = n_symbols * (uint64_t)L->bits_per_ofdm;
-  if ((L->fast == 1 || L->fast == 3) && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
+  if (L->fast != 0 && (compare_limit_bits == 0 || compare_limit_bits >= whole) && n_bytes * 8 >= whole &&
       (reinterpret_cast<uintptr_t>(bits_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(noise_dev) & 15) == 0) {
     // common link shape, whole OFDM symbols: the fast kernel streams the recorded bits and noise
     FastParams f;
@@ -615,7 +631,8 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
     f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
     f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
     f.sym_count = n_symbols;
-    return launch_fast(L, f, dump_dev != nullptr, true, false, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, L->fast == 3, (cudaStream_t)stream);
+    return launch_fast(L, f, dump_dev != nullptr, true, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, L->fast == 3,
+                       (cudaStream_t)stream);
   }
   LinkParams p;
   fill_params(L, p, snr_db);

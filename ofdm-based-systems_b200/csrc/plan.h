@@ -54,6 +54,7 @@ struct ofdm_link {
   float2* d_level = nullptr;    // fast = 2: {1/knorm_k, -(2^23 + s_k)}
   unsigned* d_mask = nullptr;   // fast = 2: packed field masks
   float2* d_psk = nullptr;      // fast = 3: PSK point table [256]
+  unsigned short* d_bitoff = nullptr;   // fast = 2: bit offset of every subcarrier inside an OFDM symbol
   float2* d_tw_fast = nullptr;  // pass-2 twiddles [(r-1)*E + k], then the pass-3 base twiddles exp(-2 pi i j / N)
   float2 taps_fast[8];
   double knorm = 1.0;

@@ -44,7 +44,8 @@ def rel_err(a, ref):
 FAST_CASES = {"headline_n1024_64qam_mmse", "c2_n1024_16qam_mmse", "c3_n64_64qam_mmse_p2", "c3_n64_64qam_zf_p2",
               "c5_n4096_256qam_mmse", "c1_n64_qpsk_cp16_awgn_zf", "cp10_n64_16qam_mmse", "rawtaps_n64_16qam_mmse", "n512_256qam_zf", "sc_n256_16qam_mmse",
               "sc_n64_qpsk_zf_p1", "zp_n256_64qam_zf", "zp_n64_16qam_mmse", "isi_cp3_n256_64qam_mmse",
-              "isi_none_n128_16qam_zf", "psk2_n64_zf_flat", "psk8_n128_mmse_two_ray"}
+              "isi_none_n128_16qam_zf", "psk2_n64_zf_flat", "psk8_n128_mmse_two_ray", "adaptive_p1_n64_mmse",
+              "adaptive_severe_n256_mmse"}
 
 
 @pytest.mark.parametrize("kernel", ["auto", "general"])
@@ -103,3 +104,42 @@ def test_replay_matches_reference(name, noise_dtype, kernel, monkeypatch):
     assert res.symbols == n_ofdm * n
     assert res.bits == min(8 * g["tx_bytes"].size, n_ofdm * link.bits_per_ofdm_symbol)
     assert abs(res.papr_db - float(g["papr_db"])) < 2e-4
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+@pytest.mark.parametrize("n,n_ofdm", [(64, 48), (1024, 8), (4096, 8)])
+def test_adaptive_replay_matches_oracle(n, n_ofdm, kernel, monkeypatch, kat):
+    """Per-subcarrier orders 0 / 4 / 16 / 64 / 256 with recorded bits and noise: symbols start at arbitrary bit offsets of the
+    byte stream (constellation/adaptive.py:178-198).  The oracle is the checker (pinned to the reference by the fixtures)."""
+    from ofdm_based_systems._native import Link
+    if kernel == "general":
+        monkeypatch.setenv("OFDM_B200_FORCE_GENERAL", "1")
+    rng = np.random.default_rng(n + 1)
+    orders = rng.choice([0, 4, 16, 64, 256], size=n, p=[0.1, 0.3, 0.25, 0.2, 0.15]).astype(np.int64)
+    orders[:4] = [256, 0, 4, 16]
+    taps_raw, snr, P = kat["chan_severe_multipath"], 27.0, 7
+    setup = oc.LinkSetup(n_sc=n, taps_raw=taps_raw, snr_db=snr, order=16, eq="MMSE", orders=orders, prefix_len_override=P)
+    bits_per = int(sum(oc.bits_per_symbol(int(o)) for o in orders if o > 1))
+    assert (bits_per * n_ofdm) % 8 == 0 and bits_per % 32 != 0          # whole bytes in total, unaligned symbols
+    tx = rng.integers(0, 256, bits_per * n_ofdm // 8, dtype=np.uint8)
+    sigma = np.sqrt(np.mean(orders > 1) / 10 ** (snr / 10) / 2)
+    noise = (rng.normal(size=n_ofdm * (n + P)) + 1j * rng.normal(size=n_ofdm * (n + P))) * sigma
+    ref = oc.run_link(setup, tx.tobytes(), bits_per * n_ofdm, noise=noise)
+    link = Link(n, setup.taps_chan, setup.H_eq, orders, prefix_type="CYCLIC", prefix_len=P, equalizer="MMSE")
+    assert link.uses_fast_kernel == (kernel == "auto")
+    res, d = link.run_replay(snr, tx.tobytes(), noise, n_ofdm, dump=("z", "rx_labels", "tx_labels"))
+    link.close()
+    act = orders > 1
+    tx_ref = np.where(act, np.asarray(ref["tx_labels"]).reshape(n_ofdm, n), 0)
+    rx_ref = np.where(act, np.asarray(ref["rx_labels"]).reshape(n_ofdm, n), 0)
+    np.testing.assert_array_equal(d["tx_labels"], tx_ref)
+    z_ref = np.asarray(ref["received_symbols"]).reshape(n_ofdm, n)
+    assert rel_err(d["z"][:, act].astype(np.complex128), z_ref[:, act]) < REL_TOL
+    dist = np.full(z_ref.shape, np.inf)
+    for k in np.nonzero(act)[0]:
+        dist[:, k] = oc.qam_boundary_distance(z_ref[:, k], int(orders[k]))
+    mismatch = (d["rx_labels"] != rx_ref) & act
+    assert not np.any(mismatch & (dist > BOUNDARY_TAU))
+    if not mismatch.any():
+        assert res.bit_errors == ref["bit_errors"] and res.symbol_errors == ref["symbol_errors"]
+    assert res.bits == bits_per * n_ofdm
