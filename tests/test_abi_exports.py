@@ -39,3 +39,20 @@ def test_no_silent_cpu_fallback():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _native.Link(64, np.ones(1, complex), np.ones(64, complex), np.full(64, 4))
+
+
+def test_header_compiles_and_links_from_plain_c(tmp_path):
+    """include/ofdm_b200.h is a C header: gcc -std=c99 -pedantic compiles a consumer, links it against the library and
+    the program runs (with a GPU it simulates 128 000 bits; without one it checks the error path)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "abi_check"
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-o", str(exe), "-L", PKG, "-lofdm_b200", f"-Wl,-rpath,{PKG}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
