@@ -272,7 +272,7 @@ def run_b200_arm(args) -> None:
                        "l2": "144 MiB (151 MB > 126 MB L2) memset between timed steps, inside the timed region; the kernel's inputs are generated in registers (86 KB of tables read per launch)"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "bits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "LinkSweep(cfg).sweep(): host taps/orders -> tables H2D -> kernel -> all-reduce -> counters D2H, per step"},
+                    "what": "LinkSweep(cfg).sweep() per step: link built from host taps / orders (tables staged in pinned memory, one H2D copy), kernel, all-reduce when N > 1, counters D2H"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak and peak > 0 else None, "traffic": traffic,

@@ -57,6 +57,28 @@ struct ArenaCache {
 };
 ArenaCache g_arenas;
 
+// Pinned host staging for the table upload of ofdm_link_create: one buffer per host thread, grown on demand.
+struct PinnedStage {
+  unsigned char* ptr = nullptr;
+  size_t bytes = 0;
+  unsigned char* reserve(size_t need) {
+    if (bytes >= need) return ptr;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    const size_t want = need < (1u << 20) ? (1u << 20) : need;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ptr), want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      ptr = nullptr;
+      return nullptr;
+    }
+    bytes = want;
+    return ptr;
+  }
+  ~PinnedStage() { if (ptr) cudaFreeHost(ptr); }
+};
+thread_local PinnedStage g_stage;
+
 }  // namespace
 
 namespace ofdm {
@@ -515,21 +537,29 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
                off_bo = off_msk + mask_host.size() * sizeof(unsigned),
                off_psk = (off_bo + bitoff_host.size() * sizeof(unsigned short) + 15) & ~size_t(15),
                total = off_psk + psk_host.size() * sizeof(float2);
-  std::vector<unsigned char> stage(total, 0);
-  std::memcpy(stage.data() + off_sc, sc.data(), N * sizeof(float4));
-  std::memcpy(stage.data() + off_eq, eq.data(), N * sizeof(float4));
-  if (!eq_fast_host.empty()) std::memcpy(stage.data() + off_eqf, eq_fast_host.data(), eq_fast_host.size() * sizeof(float4));
-  std::memcpy(stage.data() + off_tw, tw.data(), tw.size() * sizeof(float2));
-  if (!tw_fast_host.empty()) std::memcpy(stage.data() + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
-  if (!level_host.empty()) std::memcpy(stage.data() + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
-  if (!mask_host.empty()) std::memcpy(stage.data() + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
-  if (!bitoff_host.empty()) std::memcpy(stage.data() + off_bo, bitoff_host.data(), bitoff_host.size() * sizeof(unsigned short));
-  if (!psk_host.empty()) std::memcpy(stage.data() + off_psk, psk_host.data(), psk_host.size() * sizeof(float2));
+  // one pinned staging buffer -> one host->device copy
+  std::vector<unsigned char> pageable;
+  unsigned char* stage_ptr = g_stage.reserve(total);
+  if (!stage_ptr) {            // no pinned memory to be had: pageable copy
+    pageable.resize(total);
+    stage_ptr = pageable.data();
+  }
+  std::memset(stage_ptr, 0, off_sc);
+  std::memcpy(stage_ptr + off_sc, sc.data(), N * sizeof(float4));
+  std::memcpy(stage_ptr + off_eq, eq.data(), N * sizeof(float4));
+  if (!eq_fast_host.empty()) std::memcpy(stage_ptr + off_eqf, eq_fast_host.data(), eq_fast_host.size() * sizeof(float4));
+  std::memcpy(stage_ptr + off_tw, tw.data(), tw.size() * sizeof(float2));
+  if (!tw_fast_host.empty()) std::memcpy(stage_ptr + off_twf, tw_fast_host.data(), tw_fast_host.size() * sizeof(float2));
+  if (!level_host.empty()) std::memcpy(stage_ptr + off_lvl, level_host.data(), level_host.size() * sizeof(float2));
+  if (!mask_host.empty()) std::memcpy(stage_ptr + off_msk, mask_host.data(), mask_host.size() * sizeof(unsigned));
+  if (!bitoff_host.empty()) std::memcpy(stage_ptr + off_bo, bitoff_host.data(), bitoff_host.size() * sizeof(unsigned short));
+  if (!psk_host.empty()) std::memcpy(stage_ptr + off_psk, psk_host.data(), psk_host.size() * sizeof(float2));
   unsigned char* arena = g_arenas.acquire(total, dev);
   if (!arena) { cudaGetLastError(); return fail(OFDM_ENOMEM, "cudaMalloc(%zu bytes of link tables) failed", total); }
   L->arena = arena;
   L->table_bytes = total;
-  CUDA_TRY(cudaMemcpy(arena, stage.data(), total, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpyAsync(arena, stage_ptr, total, cudaMemcpyHostToDevice, nullptr));
+  CUDA_TRY(cudaStreamSynchronize(nullptr));   // the staging buffer is reused by the next creation on this thread
   L->d_cnt = reinterpret_cast<CounterBlock*>(arena);
   L->d_sc = reinterpret_cast<float4*>(arena + off_sc);
   L->d_eq = reinterpret_cast<float4*>(arena + off_eq);
