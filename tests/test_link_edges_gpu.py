@@ -87,6 +87,8 @@ def test_full_size_counters_are_additive_and_reproducible(n, order, per_launch):
     parts = [link.run_fused(24.0, sigma, b - a, seed=42, point=3, first_symbol=a) for a, b in zip(cuts, cuts[1:])]
     assert whole.bit_errors == sum(p.bit_errors for p in parts) > 0
     assert whole.symbol_errors == sum(p.symbol_errors for p in parts)
+    clean = link.run_fused(300.0, 0.0, per_launch, seed=43)       # map -> IFFT -> FIR -> FFT -> MMSE -> demap round trip
+    assert clean.bits == whole.bits and clean.bit_errors == 0 and clean.symbol_errors == 0
     far = link.run_fused(24.0, sigma, 2000, seed=42, point=3, first_symbol=(1 << 40) + 7)
     assert far.bits == 2000 * n * bps and 0 < far.bit_errors < far.bits // 4
     # BER of the two halves agree within their sampling noise (per-symbol correlated errors: generous 6 sigma)
