@@ -15,6 +15,8 @@ from typing import Any, BinaryIO, Dict, List, Optional, Type
 import numpy as np
 from numpy.typing import NDArray
 
+# The reference's callers and tests reach the component classes through this module's namespace too
+# (e.g. ``simulation.models.SerialToParallelConverter``), so every name the reference imports here is kept importable.
 from ofdm_based_systems.bits_generation.models import AdaptiveBitsGenerator, IGenerator, RandomBitsGenerator
 from ofdm_based_systems.channel.models import ChannelModel
 from ofdm_based_systems.configuration.enums import (

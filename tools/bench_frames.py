@@ -3,7 +3,6 @@ BASELINE config #4 shape (fresh Rayleigh realisation per frame, water-filling + 
 shape (N=1024 16-QAM MMSE, 8-tap Rayleigh per frame); wall time of the whole synchronous call (tap generation,
 water-filling, table build, link kernel, counters D2H)."""
 import os, sys, time
-import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "ofdm-based-systems_b200"))
 from ofdm_based_systems import _native as nat

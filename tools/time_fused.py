@@ -1,5 +1,5 @@
 """Time the fused headline launch with the device-side API: python tools/time_fused.py [N] [order] [symbols] [reps] [OFDM|SC-OFDM]"""
-import ctypes, os, sys, time
+import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "ofdm-based-systems_b200"))
