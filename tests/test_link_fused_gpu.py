@@ -200,3 +200,28 @@ def test_applied_power_loading_replays_through_oracle(n, chan, P, eq, fast, kat)
         assert res.bit_errors == ref["bit_errors"] and res.symbol_errors == ref["symbol_errors"]
     assert abs(res.papr_db - ref["papr_db"]) < 2e-4
     link.close()
+
+
+def test_noise_tails_follow_the_gaussian(kat):
+    """The in-register Box-Muller generator (32-bit radius word, tail to 6.6 sigma) against the normal tail
+    probabilities on 4e7 real samples: a BER sweep to 1e-9 lives on these tails."""
+    from scipy.stats import norm
+    from ofdm_based_systems._native import Link
+    n, P, n_ofdm, sigma = 1024, 7, 19532, 0.37
+    taps = oc.normalize_taps(kat["chan_severe_multipath"])
+    link = Link(n, taps, np.fft.fft(taps, n), np.full(n, 16), prefix_type="CYCLIC", prefix_len=P)
+    _, d = link.run_fused(12.0, sigma, n_ofdm, seed=2024, dump=("noise",))
+    link.close()
+    w = d["noise"][:, P:].reshape(-1)
+    x = np.concatenate([w.real, w.imag]).astype(np.float64) / sigma
+    m = x.size
+    assert m >= 4e7
+    assert abs(x.mean()) < 5 / np.sqrt(m) and abs(x.var() - 1) < 5 * np.sqrt(2 / m)
+    for k in (2.0, 3.0, 4.0, 4.5, 5.0):
+        p = 2 * norm.sf(k)
+        count = int(np.sum(np.abs(x) > k))
+        assert abs(count - m * p) < 5 * np.sqrt(m * p) + 1, (k, count, m * p)
+    assert np.max(np.abs(x)) < 6.7           # 32-bit radius word: the radius stops at sqrt(2 ln 2^33) = 6.76
+    # independence of neighbouring samples and of the two components
+    assert abs(np.mean(x[:-1] * x[1:])) < 5 / np.sqrt(m)
+    assert abs(np.mean(w.real * w.imag)) / sigma ** 2 < 5 / np.sqrt(m / 2)
