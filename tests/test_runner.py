@@ -42,7 +42,8 @@ def test_shipped_configs_load_unchanged():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("config", ["simulation_settings_test.json", "simulation_settings_adaptive.json"])
+@pytest.mark.parametrize("config", ["simulation_settings_test.json", "simulation_settings_adaptive.json",
+                                    "simulation_settings.json"])
 def test_runner_end_to_end(tmp_path, monkeypatch, config):
     from ofdm_based_systems.configuration.models import Settings, SimulationSettings
     from ofdm_based_systems.main import ResultsManager, SimulationRunner
@@ -58,6 +59,9 @@ def test_runner_end_to_end(tmp_path, monkeypatch, config):
     if config.endswith("test.json"):                          # 5.4e-4 @20 dB, 0 @30 dB on 409 600 bits
         assert 2e-4 < bers[0] < 1.2e-3 and bers[1] < 3e-5
         assert results[0]["total_bits"] == 409600
+    elif config == "simulation_settings.json":                # the reference's default: SC-OFDM, QPSK, ZF, 7 SNR points
+        assert results[0]["modulator_type"] == "SC_OFDM" and results[0]["total_bits"] == 2_000_000
+        assert all(a > b for a, b in zip(bers[:5], bers[1:5])) and 0.05 < bers[0] < 0.3 and bers[-1] < 1e-5
     else:                                                     # adaptive: orders per SNR as measured on the reference
         assert all(b < 5e-3 for b in bers)
         assert max(results[2]["constellation_order_per_subcarrier"]) == 64
