@@ -1,6 +1,6 @@
 """Randomised differential test on the GPU box: random link shapes through the product kernel (fused mode, dumps), the
 same bits and noise replayed through the CPU oracle and through the OTHER CUDA kernel (general), decisions and counters
-compared.      python tools/fuzz_parity.py [cases] [seed]
+compared.      python tests/fuzz_parity.py [cases] [seed]
 Test infrastructure (it imports oracle/); prints one line per case and a summary, exits non-zero on a mismatch."""
 import os, sys
 import numpy as np
