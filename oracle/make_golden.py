@@ -89,8 +89,11 @@ MAPPER = {"QAM": QAMConstellationMapper, "PSK": PSKConstellationMapper}
 
 
 def link_case(name, n_sc, order, scheme, taps_raw, prefix_type, prefix_len, eq, snr_db, n_ofdm, seed,
-              modulator="OFDM", orders=None, awgn=True, keep=("Y",)):
-    """Drive the reference's component classes exactly as simulation/models.py:454-606 does."""
+              modulator="OFDM", orders=None, awgn=True, keep=("Y",), amp=None, rx_gain=None, kind="link"):
+    """Drive the reference's component classes exactly as simulation/models.py:454-606 does.
+    ``amp`` / ``rx_gain`` (kind="loaded"): the applied power loading of the reference's experiments around its own
+    components - the two NumPy lines of examples/waterfilling_noise_bump_experiment.py:148 (parallel * sqrt(P)) and
+    :165-169 (demodulated / sqrt(P)), which Simulation.run() itself never executes (simulation/models.py:508)."""
     taps_raw = np.asarray(taps_raw, dtype=np.complex128)
     np.random.seed(seed)
     gen = Generator(PCG64(seed))
@@ -116,6 +119,8 @@ def link_case(name, n_sc, order, scheme, taps_raw, prefix_type, prefix_len, eq, 
     bits_list = read_bits_from_stream(bits)
     symbols = mapper.encode(bits)
     parallel = s2p.to_parallel(symbols, n_sc)
+    if amp is not None:
+        parallel = parallel * np.asarray(amp, dtype=np.float64)
     tx = mod.modulate(parallel)
     p = np.abs(tx) ** 2
     papr_db = 10 * np.log10(np.max(p) / np.mean(p))
@@ -123,6 +128,8 @@ def link_case(name, n_sc, order, scheme, taps_raw, prefix_type, prefix_len, eq, 
     rx = channel.transmit(serial)
     rx_par = s2p.to_parallel(rx, n_sc + prefix.prefix_length)
     demod = mod.demodulate(rx_par)
+    if rx_gain is not None:
+        demod = demod * np.asarray(rx_gain, dtype=np.float64)
     z = s2p.to_serial(demod)
     rx_stream = mapper.decode(z)
     rx_bytes = rx_stream.getvalue()
@@ -142,6 +149,10 @@ def link_case(name, n_sc, order, scheme, taps_raw, prefix_type, prefix_len, eq, 
              noise=(noise_model.noise if awgn else np.zeros(0, dtype=np.complex128)),
              rx_bytes=np.frombuffer(rx_bytes, dtype=np.uint8), received_symbols=z,
              bit_errors=int(bit_errors), symbol_errors=symbol_errors, papr_db=float(papr_db))
+    if amp is not None:
+        d["amp"] = np.asarray(amp, dtype=np.float64)
+    if rx_gain is not None:
+        d["rx_gain"] = np.asarray(rx_gain, dtype=np.float64)
     if awgn and "normals" in keep:
         d["normal_re"], d["normal_im"] = noise_model.normal_re, noise_model.normal_im
     inter = dict(symbols=symbols, tx=tx, rx=rx, Y=Y)
@@ -150,7 +161,7 @@ def link_case(name, n_sc, order, scheme, taps_raw, prefix_type, prefix_len, eq, 
             d.update(inter)
         elif k in inter:
             d[k] = inter[k]
-    path = os.path.join(OUT, f"link_{name}.npz")
+    path = os.path.join(OUT, f"{kind}_{name}.npz")
     np.savez_compressed(path, **d)
     print(f"{name:28s} bits={total_bits:7d} bit_errors={bit_errors:6d} sym_errors={symbol_errors:6d} "
           f"papr={papr_db:.3f} dB  {os.path.getsize(path) / 1024:.0f} KB")
@@ -293,6 +304,8 @@ def main():
     orders = np.array([0, 2, 4, 8, 16, 4, 0, 2] * 8, dtype=np.int64)
     link_case("adaptive_psk_n64_zf", 64, 0, "PSK", ch["two_ray"], "CYCLIC", 1, "ZF", 18.0, 24, 34, orders=orders)
 
+    loaded_cases(ch)
+
     # Simulation.run() itself
     common = dict(num_subcarriers=64, snr_db=18.0)
     sim_case("default_fixed", 41, num_symbols=64 * 40, **common)
@@ -311,5 +324,25 @@ def main():
              equalizator_type=EqualizationMethod.NONE, num_subcarriers=64, snr_db=30.0)
 
 
+def loaded_cases(ch):
+    """Applied power loading: the reference's WaterfillingPowerAllocation feeds tx amplitudes sqrt(P_k)
+    and receiver gains 1/sqrt(P_k) around the reference's own mapper / modulator / channel / decoder."""
+    for nm, n_sc, order, eq, snr, n_ofdm, seed in (("p2_n64_16qam_zf", 64, 16, "ZF", 16.0, 40, 51),
+                                                    ("severe_n1024_64qam_mmse", 1024, 64, "MMSE", 24.0, 6, 52),
+                                                    ("rayleigh_n256_16qam_mmse", 256, 16, "MMSE", 14.0, 16, 53)):
+        h = {"p2": ch["Lin-Phoong_P2"], "severe": ch["severe_multipath"], "rayleigh": ch["rayleigh_fading"]}[nm.split("_")[0]]
+        gains = np.abs(np.fft.fft(h, n_sc)) ** 2
+        power = WaterfillingPowerAllocation(1.0, gains, 10 ** (-snr / 10)).allocate()
+        power = np.maximum(power * n_sc, 1e-4)          # mean power 1 per subcarrier, floored like the experiment (:146-147)
+        amp = np.sqrt(power)
+        link_case(nm, n_sc, order, "QAM", h, "CYCLIC", len(h) - 1, eq, snr, n_ofdm, seed, amp=amp, rx_gain=1.0 / amp,
+                  kind="loaded")
+
+
 if __name__ == "__main__":
-    main()
+    if "--loaded-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        names = ["Lin-Phoong_P1", "Lin-Phoong_P2", "default_multipath", "flat_fading", "rayleigh_fading", "severe_multipath", "two_ray"]
+        loaded_cases({n: np.load(os.path.join(CHAN, n + ".npy")) for n in names})
+    else:
+        main()

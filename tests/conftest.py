@@ -24,6 +24,10 @@ def golden_link_names():
     return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "link_*.npz")))
 
 
+def golden_loaded_names():
+    return sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "loaded_*.npz")))
+
+
 def golden_sim_names():
     return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "sim_*.npz")))
 

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import ofdm_oracle as oc
-from conftest import golden_link_names, load_golden
+from conftest import golden_link_names, golden_loaded_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -143,3 +143,28 @@ def test_adaptive_replay_matches_oracle(n, n_ofdm, kernel, monkeypatch, kat):
     if not mismatch.any():
         assert res.bit_errors == ref["bit_errors"] and res.symbol_errors == ref["symbol_errors"]
     assert res.bits == bits_per * n_ofdm
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+@pytest.mark.parametrize("name", golden_loaded_names())
+def test_applied_power_loading_replay_matches_reference(name, kernel, monkeypatch):
+    """Applied power loading (tx amplitudes sqrt(P_k), receiver gains 1/sqrt(P_k)) replayed from the live reference's
+    recorded bits and noise (tests/golden/loaded_*.npz), on both kernels."""
+    from ofdm_based_systems._native import Link
+    if kernel == "general":
+        monkeypatch.setenv("OFDM_B200_FORCE_GENERAL", "1")
+    g = load_golden("loaded", name)
+    n, n_ofdm, order = int(g["n_sc"]), int(g["n_ofdm"]), int(g["order"])
+    link = Link(n, g["taps_chan"], g["H_eq"], np.full(n, order), prefix_type="CYCLIC", prefix_len=int(g["prefix_len"]),
+                equalizer=str(g["eq"]), amp=g["amp"], rx_gain=g["rx_gain"])
+    assert link.uses_fast_kernel == (kernel == "auto")
+    res, d = link.run_replay(float(g["snr_db"]), g["tx_bytes"].tobytes(), g["noise"], n_ofdm, dump=("z", "rx_labels"))
+    link.close()
+    z_ref = g["received_symbols"].reshape(n_ofdm, n)
+    assert rel_err(d["z"].astype(np.complex128), z_ref) < REL_TOL
+    rx_ref = oc.labels_from_bits(g["rx_bytes"].tobytes(), oc.bits_per_symbol(order)).reshape(n_ofdm, n)
+    mismatch = d["rx_labels"] != rx_ref
+    assert not np.any(mismatch & (oc.qam_boundary_distance(z_ref, order) > BOUNDARY_TAU))
+    if not mismatch.any():
+        assert res.bit_errors == int(g["bit_errors"]) and res.symbol_errors == int(g["symbol_errors"])
+    assert abs(res.papr_db - float(g["papr_db"])) < 2e-4

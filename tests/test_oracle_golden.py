@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import ofdm_oracle as oc
-from conftest import golden_link_names, load_golden
+from conftest import golden_loaded_names, golden_link_names, load_golden
 
 
 def _setup(g):
@@ -163,3 +163,17 @@ def test_simulation_run_matches_reference(name):
         assert r["water_level"] is None or str(g["arg_adaptive_modulation_mode"]) == "FIXED"
     else:
         assert r["water_level"] == float(g["water_level"])
+
+
+@pytest.mark.parametrize("name", golden_loaded_names())
+def test_applied_power_loading_matches_reference_components(name):
+    """the oracle's amp / rx_gain path against the live reference's components with the experiment's
+    loading lines around them (oracle/make_golden.py::loaded_cases)."""
+    g = load_golden("loaded", name)
+    setup = oc.LinkSetup(n_sc=int(g["n_sc"]), taps_raw=g["taps_raw"], snr_db=float(g["snr_db"]), order=int(g["order"]),
+                         eq=str(g["eq"]), prefix_len_override=int(g["prefix_len"]), amp=g["amp"], rx_gain=g["rx_gain"])
+    r = oc.run_link(setup, g["tx_bytes"].tobytes(), int(g["total_bits"]), noise=g["noise"])
+    assert r["bit_errors"] == int(g["bit_errors"]) and r["symbol_errors"] == int(g["symbol_errors"])
+    assert r["rx_bytes"] == g["rx_bytes"].tobytes()
+    np.testing.assert_allclose(r["received_symbols"], g["received_symbols"], rtol=0, atol=1e-12)
+    assert abs(r["papr_db"] - float(g["papr_db"])) < 1e-10
