@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   // the FIR reaches into the previous OFDM symbol.  A team then owns a CONTIGUOUS chain of symbols, carries the last 8
   // tx samples of the previous one in shared memory, and recomputes the transmitter of the symbol before its chain
   // (one "halo" pass), so the result does not depend on how the symbol range is partitioned.
-  static_assert(!ISI || (!ADAPT && !FRAMES && !SC), "ISI chains: one order, single link, OFDM");
+  static_assert(!ISI || (!ADAPT && !FRAMES), "ISI chains: one order, single link");
   // SC: single-carrier OFDM (modulation/models.py:58-91) - the constellation symbols are the time samples; the
   // receiver runs FFT -> equaliser -> IFFT, i.e. the shared transform body serves phases 1 and 2 instead of 0 and 1
   static_assert(!SC || (!ADAPT && !FRAMES), "SC-OFDM: one order on every sample, single link");
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     // OFDM: rolled, ONE copy of the transform body serves both phases (instruction cache).  SC-OFDM: unrolled, so
     // that the hand-over of the equalised spectrum in registers between phases 1 and 2 has exact live ranges.
 #pragma unroll(SC ? 3 : 1)
-    for (int phase = 0; phase < (SC ? 3 : (halo ? 1 : 2)); ++phase) {
+    for (int phase = 0; phase < (halo ? 1 : (SC ? 3 : 2)); ++phase) {
       section_sync<SYNC, BLOCK>();
       if (phase == 0) {
         // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:

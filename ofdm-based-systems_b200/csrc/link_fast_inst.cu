@@ -84,8 +84,15 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
     return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream)
                 : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream);
   }
+  if (isi && sc) {  // single-carrier OFDM with a prefix shorter than the channel memory
+    if (adapt) return fail(OFDM_EUNSUPPORTED, "inter-symbol interference with loading tables runs on the general kernel");
+    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, true, true>(L, p, stream)
+                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, true, true>(L, p, stream);
+    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, true, true>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, true, true>(L, p, stream);
+  }
   if (isi) {  // prefix shorter than the channel memory: chained symbols
-    if (adapt || sc) return fail(OFDM_EUNSUPPORTED, "inter-symbol interference with loading tables or SC-OFDM runs on the general kernel");
+    if (adapt) return fail(OFDM_EUNSUPPORTED, "inter-symbol interference with loading tables runs on the general kernel");
     if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, false, true>(L, p, stream)
                             : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, false, true>(L, p, stream);
     return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, false, true>(L, p, stream)
