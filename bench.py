@@ -5,9 +5,10 @@
 
 Metric (BASELINE.json): simulated bits/s of the fused OFDM Monte-Carlo kernel at N=1024 subcarriers,
 64-QAM, MMSE, 8-tap multipath (config/channel_models/severe_multipath.npy, CP = 7), and the fraction of
-the FP32 roofline it reaches.  A "step" is one pass of the hot path over one batch of OFDM symbols
-(1e9 simulated bits per GPU); bits and noise are generated in registers (Philox), so there is no
-input tensor to keep resident - the tables the kernel reads are 40 KB.
+the FP32 roofline it reaches.  A "step" is one pass of the hot path over one batch: the BER-vs-SNR sweep of
+SURVEY 8(d) (0:2:30 dB, 16 points, 1e9 simulated bits per point and GPU) as ONE kernel launch; bits and noise
+are generated in registers (Philox), so there is no input tensor to keep resident - the tables the kernel
+reads are 40 KB.
 
 One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for the definition of every key.
 """
@@ -28,12 +29,16 @@ sys.path.insert(0, os.path.join(ROOT, "ofdm-based-systems_b200"))
 
 N_SC, ORDER, SNR_DB, PREFIX = 1024, 64, 20.0, 7
 BITS_PER_OFDM = N_SC * 6
-BITS_PER_STEP_PER_GPU = 1_000_000_000
-SYMBOLS_PER_STEP = -(-BITS_PER_STEP_PER_GPU // BITS_PER_OFDM)          # 162 761 OFDM symbols
+BITS_PER_POINT_PER_GPU = 1_000_000_000
+SYMBOLS_PER_POINT = -(-BITS_PER_POINT_PER_GPU // BITS_PER_OFDM)        # 162 761 OFDM symbols
+SNR_GRID = [float(x) for x in range(0, 31, 2)]                         # 0:2:30 dB, 16 points
 # algorithmic flops per OFDM symbol (SURVEY 8d / BASELINE.md 4): 10 N log2 N + 8 L (N+P) + 4 (N+P) + N (2 + 14 + 8)
 F_SYM = 10 * N_SC * 10 + 8 * 8 * (N_SC + PREFIX) + 4 * (N_SC + PREFIX) + N_SC * (2 + 14 + 8)   # 197 084
-WORKLOAD = "ofdm_link_fused N=1024 64-QAM MMSE CP=7 severe_multipath(8 taps) SNR=20dB, 1e9 bits/GPU/step"
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12                   # 74.45: 148 SMs x 128 FFMA lanes x 2 x max boost
+WORKLOAD = ("ofdm_link_fused N=1024 64-QAM MMSE CP=7 severe_multipath(8 taps), BER-vs-SNR sweep 0:2:30 dB (16 points), "
+            "1e9 bits/point/GPU/step")
 METRIC = "OFDM Monte-Carlo sim bits/sec (N=1024,64-QAM,MMSE)"
+STRONG_SEED = 0x0FD3
 
 
 def headline_taps() -> np.ndarray:
@@ -92,8 +97,8 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------- CPU arms
-def _cpu_chunk(args):
-    """One bounded sample of the hot path on one host core: the oracle port of the reference chain."""
+def _port_chunk(args):
+    """One bounded sample of the hot path on one host core: the NumPy oracle port of the reference chain."""
     seed, n_ofdm = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ofdm_oracle as oc
@@ -102,8 +107,22 @@ def _cpu_chunk(args):
     rng = np.random.default_rng(seed)
     bits = oc.generate_bits(n_ofdm * BITS_PER_OFDM, rng)
     shape = (n_ofdm * (N_SC + PREFIX),)
+    t0 = time.perf_counter()
     r = oc.run_link(setup, bits, n_ofdm * BITS_PER_OFDM, normals=(rng.normal(size=shape), rng.normal(size=shape)))
-    return n_ofdm * BITS_PER_OFDM, r["bit_errors"]
+    return n_ofdm * BITS_PER_OFDM, r["bit_errors"], time.perf_counter() - t0
+
+
+def _reference_chunk(args):
+    """One bounded sample on one host core through the UNMODIFIED reference (oracle/_ref, see oracle/ref_pipeline.py).
+    The SNR point cycles through the sweep grid so that the sample covers the same workload."""
+    seed, n_ofdm = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_pipeline
+    return ref_pipeline.run_chunk((seed, n_ofdm, N_SC, ORDER, SNR_GRID[seed % len(SNR_GRID)], headline_taps()))
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "src", "ofdm_based_systems"))
 
 
 def cpu_dsp_only(n_ofdm: int = 400) -> float:
@@ -126,47 +145,67 @@ def cpu_dsp_only(n_ofdm: int = 400) -> float:
     return n_ofdm * BITS_PER_OFDM / best
 
 
-def cpu_baseline_single(budget_s: float = 12.0) -> dict:
-    """oracle port, one core, bounded sample of the same workload (reported baseline, not the target)."""
-    n_ofdm, bits, t0 = 200, 0, time.perf_counter()
-    calls = 0
-    while time.perf_counter() - t0 < budget_s:
-        b, _ = _cpu_chunk((1000 + calls, n_ofdm))
+def cpu_baseline_single(budget_s: float = 14.0) -> dict:
+    """The reference itself (oracle/_ref) on ONE host core - it is single-threaded - over a bounded sample of the same
+    workload; the NumPy port and its DSP-only figure beside it (reported baselines, not the target).  The reference runs
+    in a child process because its package has the same import name as the product's."""
+    import multiprocessing as mp
+    out = {}
+    n_port, bits, calls, t0 = 200, 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < 4.0:
+        b, _, _ = _port_chunk((1000 + calls, n_port))
         bits += b
         calls += 1
-    dt = time.perf_counter() - t0
-    return {"value": bits / dt, "unit": "bits/s", "cores": 1, "kind": "port",
-            "sample": f"{calls} x {n_ofdm} OFDM symbols ({bits} bits) of the headline workload, NumPy fp64 oracle port, {dt:.1f} s",
-            "dsp_only_value": cpu_dsp_only(),
-            "dsp_only_what": "IFFT + CP, FIR + AWGN, strip + FFT + MMSE only (no mapping / demapping), same port, 1 core"}
+    port = bits / (time.perf_counter() - t0)
+    if reference_available():
+        n_ofdm, bits, calls, t0 = 100, 0, 0, time.perf_counter()
+        with mp.get_context("spawn").Pool(1) as pool:
+            while time.perf_counter() - t0 < budget_s:
+                b, _, _ = pool.apply(_reference_chunk, ((calls, n_ofdm),))
+                bits += b
+                calls += 1
+        dt = time.perf_counter() - t0
+        out = {"value": bits / dt, "unit": "bits/s", "cores": 1, "kind": "reference",
+               "sample": f"{calls} x {n_ofdm} OFDM symbols ({bits} bits) of the headline workload cycling through the SNR grid, "
+                         f"unmodified reference component pipeline (oracle/_ref), {dt:.1f} s"}
+    else:
+        out = {"value": port, "unit": "bits/s", "cores": 1, "kind": "port",
+               "sample": "oracle/_ref absent: NumPy fp64 oracle port, 4 s of 200-symbol chunks"}
+    out.update({"port_value": port, "port_what": "NumPy fp64 oracle port of the same chain, 1 core, 4 s sample",
+                "dsp_only_value": cpu_dsp_only(),
+                "dsp_only_what": "IFFT + CP, FIR + AWGN, strip + FFT + MMSE only (no mapping / demapping), same port, 1 core"})
+    return out
 
 
 def run_reference_arm(args) -> None:
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself does not
-    travel to the GPU box) on all host cores, same metric / config; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: the unmodified package, copied
+    by oracle/build_ref.py; the NumPy port only if that copy is absent) on all host cores, one independent process per
+    core as SURVEY 8d-ii prescribes, same metric / config; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_ofdm = 100
-    per_step = cores * 2                       # chunks per step -> ~0.1 Gbit per step on 64 cores
+    use_ref = reference_available()
+    chunk, n_ofdm, kind = (_reference_chunk, 25, "reference") if use_ref else (_port_chunk, 100, "port")
+    per_step = cores                              # one chunk per core and step: ~0.3 s per step for the reference
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         for w in range(args.warmup):
-            pool.map(_cpu_chunk, [(w * 1000 + i, n_ofdm) for i in range(cores)])
+            pool.map(chunk, [(w * 1000 + i, n_ofdm) for i in range(cores)])
         t0 = time.perf_counter()
         bits = 0
-        for s in range(args.steps):
-            res = pool.map(_cpu_chunk, [(50_000 + s * 1000 + i, n_ofdm) for i in range(per_step)])
-            bits += sum(b for b, _ in res)
+        for s_ in range(args.steps):
+            res = pool.map(chunk, [(50_000 + s_ * 1000 + i, n_ofdm) for i in range(per_step)])
+            bits += sum(r[0] for r in res)
         dt = time.perf_counter() - t0
     value = bits / dt
+    what = ("unmodified reference component pipeline (oracle/_ref)" if use_ref else "NumPy fp64 oracle port of the reference chain")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bits/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "step": f"{per_step} x {n_ofdm} OFDM symbols on {cores} host processes"},
-            "cpu_baseline": {"value": value, "unit": "bits/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {per_step} chunks x {n_ofdm} OFDM symbols, NumPy fp64 oracle port of the reference chain"},
+            "cpu_baseline": {"value": value, "unit": "bits/s", "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} steps x {per_step} chunks x {n_ofdm} OFDM symbols cycling through the SNR grid, {what}"},
             "e2e": {"value": value, "unit": "bits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -194,8 +233,7 @@ def run_b200_arm(args) -> None:
                      equalizator_type="MMSE")
     sweep = LinkSweep(cfg)
     flush = torch.empty(144 << 20, dtype=torch.uint8, device=dev)          # 151 MB > 126 MB L2
-    snrs = [SNR_DB]
-    S = SYMBOLS_PER_STEP
+    snrs, K, S = SNR_GRID, len(SNR_GRID), SYMBOLS_PER_POINT
 
     def barrier():
         if world > 1:
@@ -205,15 +243,12 @@ def run_b200_arm(args) -> None:
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        # ---- warm-up: W steps (>= 3), then a FIXED number of extra steps (~0.6 s under load; the count must be
-        #      identical on every rank because each step ends in a collective) so that nvidia-smi (100 ms
-        #      period) samples the clocks this kernel actually runs at
-        w = max(args.warmup, 3) + 500
+        # ---- warm-up: W steps (>= 3) plus a FIXED number of extra steps (identical on every rank: each step ends in a
+        #      collective), ~0.5 s under load so that nvidia-smi (100 ms period) samples the clocks of this kernel
+        w = max(args.warmup, 3) + 30
         for i in range(w):
             flush.zero_()
             sweep.enqueue(snrs, S, seed=i, weak_scaling=True)
-            if i % 16 == 15:
-                torch.cuda.synchronize()
         barrier()
         # ---- timed region: EXACTLY K steps, device-timed, counters stay on the device
         launches0 = _native.launch_count()
@@ -231,18 +266,18 @@ def run_b200_arm(args) -> None:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    result = sweep.finalize(snrs, payload)[0]
-    bits_per_step = S * BITS_PER_OFDM * world
+    result = sweep.finalize(snrs, payload)
+    bits_per_step = K * S * BITS_PER_OFDM * world
     value = bits_per_step * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end through the public host API: build the link from host arrays (tables H2D), run, read back
+    # ---- end to end through the public host API: build the link from host arrays (tables H2D), run the sweep, read back
     barrier()
     h2d = d2h = 0
     t0 = time.perf_counter()
     for i in range(args.steps):
         s2 = LinkSweep(cfg)
-        r2 = s2.sweep(snrs, S, seed=200 + i, weak_scaling=True)[0]
-        h2d, d2h = s2.link.table_bytes, 8 * (9 + world)
+        s2.sweep(snrs, S, seed=200 + i, weak_scaling=True)
+        h2d, d2h = s2.link.table_bytes, (8 * (9 + world) if world > 1 else 80) * K
         s2.close()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -251,10 +286,35 @@ def run_b200_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = bits_per_step * args.steps / float(t.item())
 
+    # ---- shard invariance on the hardware: a FIXED union of work (strong scaling, seed 0x0FD3, 162 761 OFDM symbols per
+    #      point in total) split over the ranks - the bit-error counts must be the same integers for N = 1, 2, 4, 8
+    strong = sweep.sweep(snrs, S, seed=STRONG_SEED, weak_scaling=False)
+    # ---- BASELINE config #5 (N=4096, 256-QAM, MMSE, ~1e12 bits per point near the BER 1e-9 crossing), strong scaling
+    c5 = None
+    if not args.no_c5:
+        cfg5 = LinkConfig(num_subcarriers=4096, taps_raw=headline_taps(), constellation_order=256, prefix_length=PREFIX,
+                          equalizator_type="MMSE")
+        s5 = LinkSweep(cfg5)
+        n5 = 10 ** 12 // (4096 * 8)
+        s5.sweep([39.0], 4000, seed=1)
+        barrier()
+        t0 = time.perf_counter()
+        r5 = s5.sweep([39.0, 39.5], n5, seed=STRONG_SEED, weak_scaling=False)
+        torch.cuda.synchronize()
+        t5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        c5 = {"workload": "N=4096 256-QAM MMSE severe_multipath CP=7, 1e12 bits per point at 39 / 39.5 dB, symbol range split over the GPUs",
+              "bits": int(sum(r["total_bits"] for r in r5)), "seconds": float(t5.item()),
+              "bits_per_s": sum(r["total_bits"] for r in r5) / float(t5.item()),
+              "bit_errors": [int(r["bit_errors"]) for r in r5], "ber": [r["bit_error_rate"] for r in r5]}
+        s5.close()
+
     if rank == 0:
-        # roofline of the dominant kernel (ofdm_link_fast_kernel<32>): algorithmic flops / measured launch time
+        # roofline of the dominant kernel (ofdm_link_fast_kernel<32, 32, ...>, one launch per step covering the 16 points):
+        # algorithmic flops / measured launch time
         peak = _native.measure_fp32_tflops(8192)
-        achieved = F_SYM * S / (ms_kernel * 1e-3) / 1e12
+        achieved = F_SYM * S * K / (ms_kernel * 1e-3) / 1e12
         traffic = None
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(prof):
@@ -262,25 +322,33 @@ def run_b200_arm(args) -> None:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
             except (ValueError, OSError):
                 traffic = None
+        at20 = result[SNR_GRID.index(SNR_DB)]
         line = {
             "metric": METRIC, "value": value, "unit": "bits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "symbols_per_step_per_gpu": S, "bits_per_step": bits_per_step,
-                       "untimed_steps": w, "untimed_steps_why": "max(W, 3) warm-up steps + 500 so that nvidia-smi (100 ms period) samples the clocks under this load",
-                       "parallelism": f"symbol-range shards x{world}, one NCCL all-reduce per step" if world > 1 else "1 GPU (no collective)",
+            "config": {"workload": WORKLOAD, "snr_grid_db": snrs, "symbols_per_point_per_gpu": S, "bits_per_step": bits_per_step,
+                       "untimed_steps": w, "untimed_steps_why": "max(W, 3) warm-up steps + 30 (~0.5 s) so that nvidia-smi (100 ms period) samples the clocks under this load",
+                       "parallelism": f"symbol-range shards x{world}, ONE NCCL all-reduce per sweep (= per step)" if world > 1 else "1 GPU (no collective)",
                        "l2": "144 MiB (151 MB > 126 MB L2) memset between timed steps, inside the timed region; the kernel's inputs are generated in registers (86 KB of tables read per launch)"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "bits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "LinkSweep(cfg).sweep() per step: link built from host taps / orders (tables staged in pinned memory, one H2D copy), kernel, all-reduce when N > 1, counters D2H"},
+                    "what": "LinkSweep(cfg).sweep(grid) per step: link built from host taps / orders (tables staged in pinned memory, one H2D copy), ONE kernel launch for the 16 points, all-reduce when N > 1, counters D2H"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak and peak > 0 else None, "traffic": traffic,
-                         "kernel": "ofdm_link_fast_kernel<32,...> (one launch per step)", "kernel_ms": ms_kernel,
-                         "flops_per_ofdm_symbol": F_SYM, "symbols_per_launch": S,
-                         "peak_source": "FFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP32 figure)"},
-            "check": {"bit_error_rate": result["bit_error_rate"], "bits": result["total_bits"], "papr_db": result["papr_db"]},
+                         "frac": achieved / peak if peak and peak > 0 else None,
+                         "frac_nominal": achieved / FP32_NOMINAL_TFLOPS, "peak_nominal": FP32_NOMINAL_TFLOPS, "traffic": traffic,
+                         "kernel": "ofdm_link_fast_kernel<32,32,...> (one launch per step, grid = SMs x 16 SNR points)", "kernel_ms": ms_kernel,
+                         "flops_per_ofdm_symbol": F_SYM, "symbols_per_launch": S * K,
+                         "peak_source": "FFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP32 figure); "
+                                        "frac_nominal uses 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.45 TFLOP/s"},
+            "check": {"bit_error_rate_20db": at20["bit_error_rate"], "bits_20db": at20["total_bits"], "papr_db": at20["papr_db"],
+                      "strong_bit_errors": int(sum(r["bit_errors"] for r in strong)),
+                      "strong_bit_errors_per_point": [int(r["bit_errors"]) for r in strong],
+                      "strong_what": f"seed {STRONG_SEED:#x}, {S} OFDM symbols per point in TOTAL split over the GPUs: identical integers for every N"},
         }
+        if c5 is not None:
+            line["c5"] = c5
         if world == 1:
             # replay mode on device-resident recorded streams: achieved HBM GB/s, reported as a fraction
             sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -308,6 +376,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE config #5 sub-record (2 x 1e12 bits)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -101,6 +101,16 @@ int ofdm_link_run_fused(ofdm_link* link, double snr_db, double noise_sigma, uint
                         uint64_t first_symbol, uint64_t n_symbols, const ofdm_link_dump* dump,
                         ofdm_link_result* out);
 
+/* A whole BER-vs-SNR sweep of one link in ONE kernel launch: replaces the sequential loop over Simulation.run() in
+ * SimulationRunner.run_all (main.py:234-240, one Simulation per SNR from create_from_simulation_settings,
+ * simulation/models.py:155-212).  Point i runs OFDM symbols [first_symbol, first_symbol + n_symbols) at snr_db[i] /
+ * noise_sigma[i] with the Philox streams of point index first_point + i, i.e. exactly what n_points calls of
+ * ofdm_link_run_fused(point = first_point + i) would produce; the SNR point is a slice of the grid (32 points per launch,
+ * more points are queued back to back).  Synchronous, HOST arrays; out[n_points]. */
+int ofdm_link_run_sweep(ofdm_link* link, int32_t n_points, const double* snr_db, const double* noise_sigma,
+                        uint64_t seed, uint32_t first_point, uint64_t first_symbol, uint64_t n_symbols,
+                        ofdm_link_result* out);
+
 /* Replay mode with HOST buffers: identical bits / noise as fed to the reference.
  *   bits  : the BytesIO content of generate_bits (bits_generation/models.py:27-55), MSB first
  *   noise : complex noise over the serial stream, (N+P) samples per OFDM symbol, as added by
@@ -130,6 +140,14 @@ void* ofdm_link_counters_device_ptr(ofdm_link* link);
  * the power sum as doubles (exact below 2^53), the power maximum in slot 9 + rank and zeros in the other ranks' slots,
  * so that ONE SUM all-reduce combines counters, sums and maxima of all ranks.  Asynchronous on `stream`. */
 int ofdm_link_pack_counters(ofdm_link* link, double* payload_row_dev, int32_t rank, int32_t world, void* stream);
+/* Asynchronous sweep: clears the link's per-point counter blocks, queues the sweep on `stream`.  snr_db / noise_sigma
+ * are HOST arrays (read before the call returns).  ofdm_link_read_sweep synchronises the stream and returns the points
+ * of the last sweep launch; ofdm_link_pack_sweep packs them into the all-reduce payload [n_points][9 + world] (DEVICE
+ * memory, layout of ofdm_link_pack_counters per row) so that ONE all-reduce per sweep combines all ranks. */
+int ofdm_link_launch_sweep(ofdm_link* link, int32_t n_points, const double* snr_db, const double* noise_sigma,
+                           uint64_t seed, uint32_t first_point, uint64_t first_symbol, uint64_t n_symbols, void* stream);
+int ofdm_link_read_sweep(ofdm_link* link, void* stream, int32_t n_points, ofdm_link_result* out);
+int ofdm_link_pack_sweep(ofdm_link* link, double* payload_dev, int32_t rank, int32_t world, void* stream);
 /* kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t ofdm_b200_launch_count(void);
 
@@ -193,6 +211,16 @@ typedef struct ofdm_frames_desc {
 int ofdm_frames_run(const ofdm_frames_desc* desc, const double* taps, int64_t n_frames, uint64_t symbols_per_frame,
                     uint64_t seed, uint32_t point, uint64_t first_frame, ofdm_link_result* total,
                     ofdm_link_result* per_frame, int32_t* orders, double* taps_out);
+
+/* Test hooks (tests/test_frames_gpu.py): the folded fp32 tables the register-resident kernel reads, as the device
+ * holds them - for one link built on the host by ofdm_link_create (eq [N][4], level [N][2], masks [N/4], taps [8][2],
+ * taps3 [8][4]; level / masks only for links with per-subcarrier tables), and for a frame batch built on the device
+ * (eq [F][N][4], level [F][N][2], masks [F][N/4], hdr [F][ofdm_frames_header_floats()] = taps [8][2], taps3 [8][4],
+ * sigma, mmse_c, 2 pads).  Any output pointer may be NULL.  HOST buffers, synchronous. */
+int ofdm_link_debug_tables(const ofdm_link* link, float* eq, float* level, uint32_t* masks, float* taps, float* taps3);
+int ofdm_frames_debug_tables(const ofdm_frames_desc* desc, const double* taps, int64_t n_frames, uint64_t seed,
+                             uint64_t first_frame, float* eq, float* level, uint32_t* masks, float* hdr);
+int ofdm_frames_header_floats(void);
 
 /* FP32 FFMA-chain microbenchmark: returns measured TFLOP/s (2 flop per FFMA) on the current device,
  * the roofline denominator SURVEY 8(d) asks for; <0 on error. */

@@ -23,7 +23,11 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libofdm_b200.so")
 SIZES = (8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192)
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-I", INCLUDE, "-diag-suppress", "177"]
+              "-Xcompiler", "-fPIC", "-I", INCLUDE, "-diag-suppress", "177",
+              # ~200 kernel instantiations with line tables: zstd-compressed fatbins keep the library near 10 MB
+              "--compress-mode=size"]
+if os.environ.get("OFDM_FAST_EXPERIMENTS"):        # extra instantiations of the headline kernel for A/B timing
+    NVCC_FLAGS.append("-DOFDM_FAST_EXPERIMENTS")
 
 
 def _nvcc() -> str:

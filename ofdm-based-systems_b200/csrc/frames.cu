@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kFtThreads) frame_tables_kernel(const FrameTab
     const double g = H.x * H.x + H.y * H.y;
     sum_h2 += g;
     float4 e = make_float4(0.f, 0.f, 1.f, 0.f);
-    float2 lv = make_float2(0.f, -8388609.0f);
+    float2 lv = make_float2(0.f, -8388608.0f);
     if (side > 1) {
       const double knorm = sqrt(2.0 * (M - 1) / 3.0);
       const double dec = knorm / (2.0 * sqn * (side - 1));
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kFtThreads) frame_tables_kernel(const FrameTab
       if (p.equalizer == OFDM_EQ_NONE) e = make_float4((float)dec, 0.f, 1.f, top);
       else if (p.equalizer == OFDM_EQ_ZF && g == 0.0) e = make_float4((float)(dec * 1e10), 0.f, 1.f, top);
       else e = make_float4((float)(H.x * dec), (float)(H.y * dec), (float)g, top);
-      lv = make_float2((float)(1.0 / knorm), -(8388608.0f + float(side)));
+      lv = make_float2((float)(1.0 / knorm), -(8388608.0f + float(side - 1)));
       act_pow += g * inv_norm * inv_norm;                // |fft(normalised taps)_k|^2 on the active subcarriers
     }
     p.eq[f * N + k] = e;
@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kFtThreads) frame_tables_kernel(const FrameTab
     for (int l = 0; l < kFastTaps; ++l)
       hd.taps[l] = l < p.n_taps ? make_float2((float)(taps[l].x * inv_norm / sqn), (float)(taps[l].y * inv_norm / sqn))
                                 : make_float2(0.f, 0.f);
+    for (int l = 0; l < kFastTaps; ++l)   // same float arithmetic as fill_fast() in ofdm_b200.cu
+      hd.taps3[l] = make_float4(hd.taps[l].x, hd.taps[l].y - hd.taps[l].x, hd.taps[l].x + hd.taps[l].y, 0.f);
     hd.sigma = (float)sqrt((a / N) / p.snr_lin / 2.0);   // noise/models.py:14-20 with the analytic stream power
     const double mean_h2 = h2 / N;
     hd.mmse_c = p.equalizer != OFDM_EQ_MMSE ? 0.f : mean_h2 == 0.0 ? INFINITY : (float)(1.0 / (double(N) * double(N) * p.snr_lin * mean_h2));
@@ -164,9 +166,17 @@ thread_local DeviceArena g_arena;
 
 using namespace ofdm;
 
-extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, int64_t n_frames, uint64_t symbols_per_frame,
-                               uint64_t seed, uint32_t point, uint64_t first_frame, ofdm_link_result* total,
-                               ofdm_link_result* per_frame, int32_t* orders_out, double* taps_out) {
+namespace {
+struct FrameTableDump {   // test hook: the per-frame tables as the device built them (HOST buffers, any may be null)
+  float* eq;              // [F][N][4]
+  float* level;           // [F][N][2]
+  uint32_t* masks;        // [F][N/4]
+  float* hdr;             // [F][sizeof(FrameHeader) / 4]
+};
+
+int frames_run_impl(const ofdm_frames_desc* d, const double* taps, int64_t n_frames, uint64_t symbols_per_frame,
+                    uint64_t seed, uint32_t point, uint64_t first_frame, ofdm_link_result* total,
+                    ofdm_link_result* per_frame, int32_t* orders_out, double* taps_out, const FrameTableDump* dump) {
   if (!d || !total) return fail(OFDM_EINVAL, "null argument");
   const int N = d->n_subcarriers, L = d->n_taps, P = d->prefix_len;
   if (!fast_supports_n(N)) return fail(OFDM_EUNSUPPORTED, "frame batches need n_subcarriers = a power of two in 64..4096, got %d", N);
@@ -257,6 +267,14 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
   count_launch();
   CUDA_TRY(cudaGetLastError());
 
+  if (dump) {
+    if (dump->eq) CUDA_TRY(cudaMemcpyAsync(dump->eq, tp.eq, F * N * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    if (dump->level) CUDA_TRY(cudaMemcpyAsync(dump->level, tp.level, F * N * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    if (dump->masks) CUDA_TRY(cudaMemcpyAsync(dump->masks, tp.masks, F * (N / 4) * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    if (dump->hdr) CUDA_TRY(cudaMemcpyAsync(dump->hdr, tp.hdr, F * sizeof(FrameHeader), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+
   // pass-2 / pass-3 twiddles of the fast transform (same table as ofdm_link_create builds)
   const std::vector<float2> tw = build_fast_twiddles(N);
   float2* d_tw = reinterpret_cast<float2*>(a + o_tw);
@@ -311,3 +329,19 @@ extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, in
   }
   return OFDM_OK;
 }
+}  // namespace
+
+extern "C" int ofdm_frames_run(const ofdm_frames_desc* d, const double* taps, int64_t n_frames, uint64_t symbols_per_frame,
+                               uint64_t seed, uint32_t point, uint64_t first_frame, ofdm_link_result* total,
+                               ofdm_link_result* per_frame, int32_t* orders_out, double* taps_out) {
+  return frames_run_impl(d, taps, n_frames, symbols_per_frame, seed, point, first_frame, total, per_frame, orders_out, taps_out, nullptr);
+}
+
+extern "C" int ofdm_frames_debug_tables(const ofdm_frames_desc* d, const double* taps, int64_t n_frames, uint64_t seed,
+                                        uint64_t first_frame, float* eq, float* level, uint32_t* masks, float* hdr) {
+  const FrameTableDump dump{eq, level, masks, hdr};
+  ofdm_link_result total;
+  return frames_run_impl(d, taps, n_frames, 1, seed, 0, first_frame, &total, nullptr, nullptr, nullptr, &dump);
+}
+
+extern "C" int ofdm_frames_header_floats(void) { return (int)(sizeof(FrameHeader) / sizeof(float)); }

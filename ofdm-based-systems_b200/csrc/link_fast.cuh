@@ -34,18 +34,25 @@ constexpr int kFastTaps = 8;
 
 struct FrameHeader {       // per channel realisation (built on the device by frames.cu)
   float2 taps[kFastTaps];  // unit-energy taps / sqrt(N)
+  float4 taps3[kFastTaps]; // {h_re, h_im - h_re, h_re + h_im, -} of the same taps (FastParams::taps3)
   float sigma;             // per-component noise standard deviation
   float mmse_c;            // as FastParams::mmse_c
   float pad[2];
 };
 
+constexpr int kMaxSweepPoints = 32;   // SNR points per launch (the parameter block carries their table)
+
+struct SweepPoint {          // one SNR point of a launch (grid y index)
+  float sigma;              // per-component noise standard deviation
+  float mmse_c;             // MMSE: sigma2 = mmse_c * sum_k |Y~_k|^2 (Y~ = unscaled FFT output); else 0
+};
+
 struct FastParams {
   float2 taps[kFastTaps];   // unit-energy taps / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1), IFFT unscaled)
+  float4 taps3[kFastTaps];  // the same taps as {h_re, h_im - h_re, h_re + h_im, -}: three real products per complex one
   const float4* eq_tab;     // {Re A, Im A, G, -}: decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1)
   const float2* tw;         // pass-2 twiddles exp(-2 pi i k r / E^2) at [k*(E+2) + r-1], then (T > E) the pass-3 base
                             // twiddles exp(-2 pi i j / N), j < N / (T/E)   (build_fast_twiddles, link_fast.cu)
-  float sigma;              // per-component noise standard deviation
-  float mmse_c;             // MMSE: sigma2 = mmse_c * sum_k |Y~_k|^2 (Y~ = unscaled FFT output); else unused
   float slice_top;          // s-1
   float tx_scale2;          // |tx|^2 = tx_scale2 * |x~|^2 (PAPR statistics)
   float z_unscale;          // DUMP only: Z = (Y~ conj A / (G + sigma2)) * z_unscale   (= 2 (s-1) / k)
@@ -56,10 +63,12 @@ struct FastParams {
   unsigned int field_mask;  // (s-1) << 1 replicated in every byte
   unsigned long long seed;
   unsigned int point;
+  // n_points >= 1 SNR points in one grid: the blocks with blockIdx.y = pt run point `point + pt` with point_tab[pt] and
+  // add into counters + 10 * pt (one CounterBlock per point)
+  unsigned int n_points;
+  SweepPoint point_tab[kMaxSweepPoints];
   unsigned long long sym_begin, sym_count;
-  unsigned long long* counters;
-  double* tx_power_sum;
-  unsigned long long* tx_power_max_bits;
+  unsigned long long* counters;   // CounterBlock(s): 8 counters, power sum (double), power max (double bits)
   float2* dump_z;
   unsigned short* dump_rx;
   unsigned short* dump_tx;
@@ -74,7 +83,7 @@ struct FastParams {
   const unsigned short* bit_offsets; // [N]: bit offset of subcarrier k inside an OFDM symbol (ADAPT + REPLAY)
   unsigned int bits_per_ofdm;        // sum of the per-subcarrier bits (ADAPT + REPLAY)
   const unsigned int* field_masks;   // [(E/4) * T]: word j of lane t = ((s_k - 1) << 1) in byte i for k = t + T (4 j + i)
-  const float2* level_tab;           // [N]: {g_k, -(2^23 + s_k)} with g_k = 1 / sqrt(2 (M_k - 1) / 3)  (0 when silent);
+  const float2* level_tab;           // [N]: {g_k, -(2^23 + s_k - 1)} with g_k = 1 / sqrt(2 (M_k - 1) / 3)  (0 when silent);
                                      // the slicer's s_k - 1 is the 4th component of eq_tab
   // PSK instantiation (constellation/models.py:356-474): labels of psk_bits bits, one per byte of the packed words
   const float2* psk_tab;    // [256]: label -> exp(j 2 pi gray^-1(label) / M)
@@ -169,6 +178,58 @@ __device__ __forceinline__ float2 fast_noise(uint32_t wr, uint32_t wa, uint32_t 
   return make_float2(rad * __cosf(ang), rad * __sinf(ang));
 }
 
+// Same distribution from ONE 32-bit word: radius field = top 20 bits, angle field = low 12 bits.
+//   u = (w | 0xFFF) 2^-32 in (0, 1]: radius^2 = c2 (lg2(w | 0xFFF) - 32), c2 = -2 sigma^2 ln 2, c2m = -32 c2 (biased by
+//   2^-18 so that the approximate lg2 cannot produce a negative argument).  A radius field of 0 (probability 2^-20) only
+//   says u < 2^-20: noise_refill() then replaces the sample by one whose u comes from 32 fresh bits, so the tail
+//   continues to u = 2^-53 (8.6 sigma) like a generator with a 52-bit radius word.
+//   angle = 2 pi (a + 0.5) / 4096 - pi via the mantissa of 2^23 + a: 4096 equally spaced rays are invisible after any
+//   projection (the radius is continuous) and noise is rotation invariant.
+constexpr uint32_t kRefillBelow = 4096u;   // w < 4096  <=>  radius field == 0
+__device__ __forceinline__ float noise20_radius(uint32_t w, float c2, float c2m) {
+  return fast_sqrt(fmaf(c2, fast_lg2((float)(w | 0xFFFu)), c2m));
+}
+__device__ __forceinline__ float2 noise20_dir(uint32_t w) {
+  const float f = __uint_as_float((w & 0xFFFu) | 0x4B000000u);                                   // 2^23 + a
+  const float ang = fmaf(f, 1.5339807878856412e-03f, -12871.104692850697f);                      // (2 pi / 4096)(a + 0.5) - pi (offset for the ROUNDED slope)
+  return make_float2(__cosf(ang), __sinf(ang));
+}
+__device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m) {
+  const float rad = noise20_radius(w, c2, c2m);
+  const float2 d = noise20_dir(w);
+  return make_float2(rad * d.x, rad * d.y);
+}
+
+// Rare path of the 32-bit-per-sample noise: at least one of this lane's E radius fields was 0.  Regenerates the lane's
+// words, and for every sample with a zero field draws 32 fresh bits r: u = (r + 0.5) 2^-52, same direction; the FIR
+// output in `row` already holds the coarse sample, so the difference is added.
+template <int E, int NROUNDS>
+__device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, uint32_t gs_hi, uint32_t point, PhiloxKey key,
+                                          float c2, float c2m, float2* dump_noise, unsigned long long dump_base) {
+#pragma unroll 1
+  for (int c = 0; c < E / 8; ++c) {
+    const uint32_t q2 = 2u * uint32_t((E / 8) * t + c);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const uint4 w4 = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q2 + h), point), key);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w = j == 0 ? w4.x : j == 1 ? w4.y : j == 2 ? w4.z : w4.w;
+        if (w >= kRefillBelow) continue;
+        const int i = 8 * c + 4 * h + j;
+        const uint4 r = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (1u << 20) | uint32_t(E * t + i), point), key);
+        const float u = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r + 0.5) 2^-32
+        const float rad_new = fast_sqrt(c2 * (fast_lg2(u) - 20.0f));
+        const float rad_old = noise20_radius(w, c2, c2m);
+        const float2 d = noise20_dir(w);
+        const float2 o = row[i];
+        row[i] = make_float2(fmaf(rad_new - rad_old, d.x, o.x), fmaf(rad_new - rad_old, d.y, o.y));
+        if (dump_noise) dump_noise[dump_base + i] = make_float2(rad_new * d.x, rad_new * d.y);
+      }
+    }
+  }
+}
+
 // Zero-padding guard interval, overlap-add at the receiver (prefix/models.py:71-101): the noise of tail sample N + n
 // lands on sample n < P.  `row` holds this lane's samples E t .. E t + E - 1; one Philox call per folded sample.
 template <int E, int NROUNDS>
@@ -189,9 +250,18 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   return x;
 }
 
+// OPT bits (measured one by one on the headline shape, profiles/r2_fast_kernel_history.md):
+//   1  noise from 32 bits per complex sample (2 Philox calls per 8 samples + rare refill) instead of 48 (3 calls)
+//   2  FIR with three real products per complex tap (Gauss) instead of four
+constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptDefault = 3;
+
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
-          bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2>
-__global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams p) {
+          bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2,
+          int TAPS = kFastTaps, int OPT = kOptDefault>
+__global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
+  // TAPS: channel taps the FIR evaluates (the host zero-pads the tap table, so a shorter loop only drops exact zeros)
+  static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || (!ISI && !FRAMES)), "tap count");
+  constexpr bool NOISE32 = (OPT & kOptNoise32) != 0, GAUSS = (OPT & kOptGaussFir) != 0;
   // PSK: M-ary phase-shift keying, one order on every subcarrier; labels through a shared-memory point table at the
   // transmitter, angle rounding at the receiver (the equaliser's positive real denominator does not move the angle)
   static_assert(!PSK || (!ADAPT && !FRAMES && !SC && !ISI), "PSK: one order, single link, OFDM, no ISI");
@@ -245,10 +315,15 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
   // symbols of this pass: s = s_lo + it * s_stride + s_first < s_hi, global index sym_base + s.  One pass over the
   // launch's range, or (FRAMES) one pass per (frame, chunk) unit with the whole block on the same frame.
   unsigned long long s_lo = 0, s_hi = p.sym_count, sym_base = p.sym_begin;
-  unsigned long long s_stride = (unsigned long long)gridDim.x * G::TEAMS;
-  unsigned long long s_first = (unsigned long long)blockIdx.x * G::TEAMS + team_in_block;
-  float noise_c2 = -1.3862943611198906f * p.sigma * p.sigma;
-  float mmse_c = p.mmse_c;
+  // the SNR point of this block is the grid's y index (block-uniform: everything derived from it lives in uniform
+  // registers / the constant bank); a single-point launch is a sweep of one
+  const uint32_t point = p.point + blockIdx.y;
+  float mmse_c = FRAMES ? 0.f : p.point_tab[blockIdx.y].mmse_c;
+  // 32-bit team indices and iteration counts: the host splits launches so that a team sees fewer than 2^32 symbols
+  unsigned s_stride = gridDim.x * G::TEAMS;
+  unsigned s_first = blockIdx.x * G::TEAMS + team_in_block;
+  float noise_c2 = FRAMES ? 0.f : -1.3862943611198906f * p.point_tab[blockIdx.y].sigma * p.point_tab[blockIdx.y].sigma;   // -2 sigma^2 ln 2
+  [[maybe_unused]] float noise_c2m = -32.000003814697266f * noise_c2;   // see noise20_radius()
   const float2* level_tab = p.level_tab;
   __shared__ FrameHeader s_hdr;
   [[maybe_unused]] unsigned long long unit = blockIdx.x;
@@ -313,7 +388,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
       }
     }
   };
-  if constexpr (!ISI) replay_prefetch(s_first);
+  if constexpr (!ISI) replay_prefetch((unsigned long long)s_first);
 
   auto flush_counters = [&](unsigned long long* counters, double* power_sum, unsigned long long* power_max_bits) {
     // ---- counters: warp shuffle, one atomic per warp
@@ -361,6 +436,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
       load_masks(p.field_masks + f * (N / 4));
       level_tab = p.level_tab + f * N;
       noise_c2 = -1.3862943611198906f * s_hdr.sigma * s_hdr.sigma;
+      noise_c2m = -32.000003814697266f * noise_c2;
       mmse_c = s_hdr.mmse_c;
       cur_frame = (long long)f;
     }
@@ -370,23 +446,23 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     s_first = team_in_block;
     sym_base = p.sym_begin + f * p.frame_syms;
   }
-  unsigned long long iters = s_hi > s_lo ? (s_hi - s_lo + s_stride - 1) / s_stride : 0;
+  unsigned iters = s_hi > s_lo ? (unsigned)((s_hi - s_lo + s_stride - 1) / s_stride) : 0u;
   // ISI: contiguous chain [chain_lo, chain_hi) per team, preceded by the halo pass of symbol chain_lo - 1
   [[maybe_unused]] unsigned long long chain_lo = 0, chain_hi = 0;
   [[maybe_unused]] bool has_prev = false;
   if constexpr (ISI) {
     const unsigned long long per = iters;                 // = ceil(sym_count / teams)
-    chain_lo = s_first * per < s_hi ? s_first * per : s_hi;
+    chain_lo = (unsigned long long)s_first * per < s_hi ? (unsigned long long)s_first * per : s_hi;
     chain_hi = chain_lo + per < s_hi ? chain_lo + per : s_hi;
     has_prev = chain_lo < chain_hi && sym_base + chain_lo > 0;
-    iters = per + 1;
+    iters = (unsigned)per + 1u;
     if (t < G::TAIL_F2) s_tail[t] = make_float2(0.f, 0.f);
     replay_prefetch(has_prev ? chain_lo - 1 : chain_lo);
   }
-  for (unsigned long long it = 0; it < iters; ++it) {
+  for (unsigned it = 0; it < iters; ++it) {
     const bool halo = ISI && it == 0;
     const unsigned long long s = ISI ? (halo ? (has_prev ? chain_lo - 1 : chain_lo) : chain_lo + it - 1)
-                                     : s_lo + it * s_stride + s_first;
+                                     : s_lo + (unsigned long long)it * s_stride + s_first;
     const bool active = ISI ? (!halo && s < chain_hi) : s < s_hi;
     const unsigned long long gs = sym_base + ((active || (halo && has_prev)) ? s : s_lo);
     const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
@@ -486,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         } else {
 #pragma unroll
           for (int c = 0; c < CALLS; ++c) {
-            const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), p.point), key);
+            const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), point), key);
             const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -503,9 +579,9 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             }
           }
         }
-        // level = 2*index - (s-1) as float via the mantissa of 2^23 + (2*index + 1); re/im swapped so the
+        // level = 2*index - (s-1) as float via the mantissa of 2^23 + 2*index; re/im swapped so the
         // forward FFT below computes the inverse transform
-        const float cen = -(magic + p.slice_top + 1.0f);
+        const float cen = -(magic + p.slice_top);
         if constexpr (PSK) {
 #pragma unroll
           for (int m = 0; m < E; ++m) {
@@ -515,10 +591,10 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         }
 #pragma unroll
         for (int m = 0; m < (PSK ? 0 : E); ++m) {
-          const unsigned fc = __byte_perm(txc[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
-          const unsigned fr = __byte_perm(txr[m >> 2] | 0x01010101u, 0x4B000000u, 0x7650 + (m & 3));
+          const unsigned fc = __byte_perm(txc[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
+          const unsigned fr = __byte_perm(txr[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
           if constexpr (ADAPT) {
-            // per-subcarrier side s_k and power normalisation: (f - (2^23 + s_k)) is the exact integer level
+            // per-subcarrier side s_k and power normalisation: (f - (2^23 + s_k - 1)) is the exact integer level
             const float2 g = __ldg(&level_tab[t + T * m]);
             v[m] = make_float2(-(__uint_as_float(fr) + g.y) * g.x, (__uint_as_float(fc) + g.y) * g.x);
           } else {
@@ -555,6 +631,12 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
         if constexpr (ISI) {
           if (t < G::TAIL_F2) s_tail[t] = new_tail;   // read again only in the next symbol's channel phase
         }
+        [[maybe_unused]] uint32_t wmin = 0xffffffffu;   // NOISE32: smallest noise word of this lane (refill test)
+        [[maybe_unused]] float ps[8];                   // GAUSS: re + im of the halo samples
+        if constexpr (GAUSS) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ps[i] = prev[i].x + prev[i].y;
+        }
 #pragma unroll FIR_UNROLL
         for (int c = 0; c < E / 8; ++c) {
           float2 cur[8], y[8];
@@ -564,28 +646,67 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
             cur[i] = make_float2(q.x, q.y);
             cur[i + 1] = make_float2(q.z, q.w);
           }
+          if constexpr (GAUSS) {
+            // h x = (k1 - k3) + j (k1 + k2) with k1 = h_re (x_re + x_im), k2 = (h_im - h_re) x_re, k3 = (h_re + h_im) x_im:
+            // three sums over the taps, every product a 2-register FFMA with the tap in the constant bank
+            float cs[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float yr = 0.f, yi = 0.f;
+            for (int i = 0; i < 8; ++i) cs[i] = cur[i].x + cur[i].y;
 #pragma unroll
-            for (int l = 0; l < kFastTaps; ++l) {
-              const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
-              const float2 h = FRAMES ? s_hdr.taps[l] : p.taps[l];
-              yr = fmaf(h.x, x.x, yr);
-              yr = fmaf(-h.y, x.y, yr);
-              yi = fmaf(h.x, x.y, yi);
-              yi = fmaf(h.y, x.x, yi);
+            for (int i = 0; i < 8; ++i) {
+              float k1 = 0.f, k2 = 0.f, k3 = 0.f;
+#pragma unroll
+              for (int l = 0; l < TAPS; ++l) {
+                const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
+                const float xs = (i - l >= 0) ? cs[i - l] : ps[8 + i - l];
+                const float4 h = FRAMES ? s_hdr.taps3[l] : p.taps3[l];
+                k1 = fmaf(h.x, xs, k1);
+                k2 = fmaf(h.y, x.x, k2);
+                k3 = fmaf(h.z, x.y, k3);
+              }
+              y[i] = make_float2(k1 - k3, k1 + k2);
             }
-            y[i] = make_float2(yr, yi);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ps[i] = cs[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float yr = 0.f, yi = 0.f;
+#pragma unroll
+              for (int l = 0; l < TAPS; ++l) {
+                const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
+                const float2 h = FRAMES ? s_hdr.taps[l] : p.taps[l];
+                yr = fmaf(h.x, x.x, yr);
+                yr = fmaf(-h.y, x.y, yr);
+                yi = fmaf(h.x, x.y, yi);
+                yi = fmaf(h.y, x.x, yi);
+              }
+              y[i] = make_float2(yr, yi);
+            }
           }
           {  // unconditional (sigma = 0 scales the samples to zero): keeping FIR and noise in ONE basic block
              // lets ptxas interleave the Philox / MUFU chains with the FIR's FFMAs
-            if constexpr (!REPLAY) {
+            if constexpr (!REPLAY && NOISE32) {
+              // 8 complex samples from 2 Philox calls: one word per sample (20-bit radius field, 12-bit angle field)
+              const uint32_t q2 = 2u * uint32_t((E / 8) * t + c);
+              const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q2, point), key);
+              const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q2 + 1u), point), key);
+              const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+              wmin = min(min(wmin, min(w8[0], w8[1])), min(min(w8[2], w8[3]), min(min(w8[4], w8[5]), min(w8[6], w8[7]))));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 g = fast_noise20(w8[i], noise_c2, noise_c2m);
+                if constexpr (DUMP) {
+                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
+                }
+                y[i] = cadd(y[i], g);
+              }
+            } else if constexpr (!REPLAY) {
               // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
               const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
-              const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, p.point), key);
-              const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), p.point), key);
-              const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), p.point), key);
+              const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, point), key);
+              const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), point), key);
+              const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), point), key);
               const uint32_t rw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
               const uint32_t aw[4] = {wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
@@ -604,9 +725,14 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
 #pragma unroll
           for (int i = 0; i < 8; ++i) prev[i] = cur[i];
         }
+        if constexpr (!REPLAY && NOISE32) {
+          if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line
+            noise_refill<E, NROUNDS>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
+                                     s * (unsigned long long)(N + P) + noise_off + E * t);
+        }
         if constexpr (!REPLAY) {
           if (p.zero_prefix)   // rare link shape: kept out of line so that the hot instruction stream stays small
-            zero_prefix_tail_noise<E, NROUNDS>(row, t, P, gs_lo, gs_hi, p.point, key, noise_c2,
+            zero_prefix_tail_noise<E, NROUNDS>(row, t, P, gs_lo, gs_hi, point, key, noise_c2,
                                                (DUMP && active) ? p.dump_noise : nullptr, s * (unsigned long long)(N + P) + N);
         }
         tsync();
@@ -826,10 +952,8 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
           const unsigned dc = ((rxc[j] - K) ^ txc[j]) & 0x1E1E1E1Eu;
           const unsigned dr = ((rxr[j] - K) ^ txr[j]) & 0x1E1E1E1Eu;
           be += __popc(inv_gray_fields(dc) & 0x1E1E1E1Eu) + __popc(inv_gray_fields(dr) & 0x1E1E1E1Eu);
-          unsigned any = dc | dr;
-          any |= any >> 2;
-          any |= any >> 1;
-          se += __popc(any & 0x02020202u);
+          // a byte of dc | dr is at most 0x1E: adding 0x7F sets its bit 7 exactly when it is non-zero, without carries
+          se += __popc(((dc | dr) + 0x7F7F7F7Fu) & 0x80808080u);
           if constexpr (DUMP) {
             if (active) {
 #pragma unroll
@@ -869,7 +993,10 @@ __global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const FastParams 
     unit += gridDim.x;
   }
   } while (FRAMES);
-  if constexpr (!FRAMES) flush_counters(p.counters, p.tx_power_sum, p.tx_power_max_bits);
+  if constexpr (!FRAMES) {
+    unsigned long long* cb = p.counters + 10ull * blockIdx.y;
+    flush_counters(cb, reinterpret_cast<double*>(cb + 8), cb + 9);
+  }
 }
 
 }  // namespace ofdm

@@ -19,13 +19,9 @@ int launch_frames_shape<OFDM_FAST_E, OFDM_FAST_T>(int sms, const FastParams& p0,
   constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T, BLOCK = 512, SYNC = T > 32 ? 0 : 2;
   using G = FastGeometry<E, T, BLOCK>;
   auto kern = ofdm_link_fast_kernel<E, T, false, true, false, BLOCK, SYNC, true, true>;
-  static int occ = 0;
-  if (occ == 0) {
-    if (G::SMEM_BYTES > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::BLOCK, G::SMEM_BYTES));
-    if (occ <= 0) occ = 1;
-  }
+  int occ = 1;
+  const int rc = blocks_per_sm(kern, G::BLOCK, G::SMEM_BYTES, &occ);
+  if (rc != OFDM_OK) return rc;
   FastParams p = p0;
   // split a frame into chunks (multiples of the symbols a block holds in flight) until every SM has ~2 units
   const unsigned long long slots = (unsigned long long)sms * occ, S = p.frame_syms;
@@ -46,25 +42,32 @@ int launch_frames_shape<OFDM_FAST_E, OFDM_FAST_T>(int sms, const FastParams& p0,
   return OFDM_OK;
 }
 
-template <int E, int T, bool DUMP, bool REPLAY, int BLOCK = 512, int SYNC = 2, bool ADAPT = false, bool SC = false,
-          bool ISI = false, bool PSK = false>
-static int launch_fast_kernel(const ofdm_link* L, const FastParams& p, cudaStream_t stream) {
+template <int E, int T, bool DUMP, bool REPLAY, bool ADAPT = false, bool SC = false, bool ISI = false, bool PSK = false,
+          int TAPS = kFastTaps, int SYNC = (T > 32 ? 0 : 2), int OPT = kOptDefault>
+static int launch_fast_kernel(const ofdm_link* L, const FastParams& p0, cudaStream_t stream) {
+  constexpr int BLOCK = 512;
   using G = FastGeometry<E, T, BLOCK>;
-  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT, false, SC, ISI, PSK>;
-  static int occ = 0;   // per process: attribute + occupancy query cost ~0.1 ms each
-  if (occ == 0) {
-    if (G::SMEM_BYTES > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::BLOCK, G::SMEM_BYTES));
-    if (occ <= 0) occ = 1;
+  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT, false, SC, ISI, PSK, 10, 2, TAPS, OPT>;
+  int occ = 1;
+  const int rc = blocks_per_sm(kern, G::BLOCK, G::SMEM_BYTES, &occ);
+  if (rc != OFDM_OK) return rc;
+  const unsigned long long need = (p0.sym_count + G::TEAMS - 1) / G::TEAMS;
+  unsigned long long per_point = (unsigned long long)L->sms * occ;
+  if (need < per_point) per_point = need;
+  if (per_point == 0) return OFDM_OK;
+  const unsigned points = p0.n_points > 1 ? p0.n_points : 1;
+  // the kernel counts a team's symbols in 32 bits: ranges beyond 2^40 symbols are queued in pieces (same counters;
+  // contiguous pieces keep an inter-symbol-interference chain intact because every piece recomputes its halo symbol)
+  constexpr unsigned long long kPiece = 1ull << 40;
+  for (unsigned long long done = 0; done < p0.sym_count; done += kPiece) {
+    FastParams p = p0;
+    p.sym_begin = p0.sym_begin + done;
+    p.sym_count = p0.sym_count - done < kPiece ? p0.sym_count - done : kPiece;
+    if (REPLAY && done) return fail(OFDM_EUNSUPPORTED, "recorded streams longer than 2^40 OFDM symbols");
+    kern<<<dim3((unsigned)per_point, points), G::BLOCK, G::SMEM_BYTES, stream>>>(p);
+    count_launch();
+    CUDA_TRY(cudaGetLastError());
   }
-  const unsigned long long need = (p.sym_count + G::TEAMS - 1) / G::TEAMS;
-  unsigned long long grid = (unsigned long long)L->sms * occ;
-  if (need < grid) grid = need;
-  if (grid == 0) return OFDM_OK;
-  kern<<<(unsigned)grid, G::BLOCK, G::SMEM_BYTES, stream>>>(p);
-  count_launch();
-  CUDA_TRY(cudaGetLastError());
   return OFDM_OK;
 }
 
@@ -72,56 +75,51 @@ template <int E, int T>
 int launch_fast_shape(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi,
                       bool psk, cudaStream_t stream);
 
+// Instantiations per team shape.  The headline path (one QAM order, OFDM, guard interval >= channel memory, Philox bits and
+// noise, counters only) exists for 1, 4 and 8 evaluated taps; every other link shape has a counters-only fused kernel
+// and ONE dump-capable kernel per input mode (recorded streams always run through the dump-capable one, its dump
+// pointers may be null), except the headline shape whose recorded-stream path is the HBM-bandwidth benchmark.
 template <>
 int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
                                                 bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream) {
   constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T;
-  constexpr int SYNC_DEFAULT = T > 32 ? 0 : 2;
-  if (psk) {  // M-ary PSK, one order
-    if (adapt || sc || isi) return fail(OFDM_EUNSUPPORTED, "this PSK link shape runs on the general kernel");
-    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream)
-                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream);
-    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, false, false, true>(L, p, stream);
-  }
-  if (isi && sc) {  // single-carrier OFDM with a prefix shorter than the channel memory
-    if (adapt) return fail(OFDM_EUNSUPPORTED, "inter-symbol interference with loading tables runs on the general kernel");
-    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, true, true>(L, p, stream)
-                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, true, true>(L, p, stream);
-    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, true, true>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, true, true>(L, p, stream);
-  }
-  if (isi) {  // prefix shorter than the channel memory: chained symbols
-    if (adapt) return fail(OFDM_EUNSUPPORTED, "inter-symbol interference with loading tables runs on the general kernel");
-    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, false, true>(L, p, stream)
-                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, false, true>(L, p, stream);
-    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, false, true>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, false, true>(L, p, stream);
-  }
-  if (sc) {  // single-carrier OFDM: one order on every sample
-    if (adapt) return fail(OFDM_EUNSUPPORTED, "SC-OFDM with per-sample orders runs on the general kernel");
-    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, false, true>(L, p, stream)
-                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, false, true>(L, p, stream);
-    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, false, true>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, false, true>(L, p, stream);
-  }
-  if (adapt) {  // per-subcarrier orders / applied power loading
-    if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT, true>(L, p, stream)
-                            : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT, true>(L, p, stream);
-    return dump ? launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT, true>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, 512, SYNC_DEFAULT, true>(L, p, stream);
-  }
-  if (replay) return dump ? launch_fast_kernel<E, T, true, true, 512, SYNC_DEFAULT>(L, p, stream)
-                          : launch_fast_kernel<E, T, false, true, 512, SYNC_DEFAULT>(L, p, stream);
-  if (dump) return launch_fast_kernel<E, T, true, false, 512, SYNC_DEFAULT>(L, p, stream);
+  if ((psk && (adapt || sc || isi)) || (adapt && (sc || isi)))
+    return fail(OFDM_EUNSUPPORTED, "this link shape runs on the general kernel");
+#define OFDM_FAST_VARIANT(ADAPT_, SC_, ISI_, PSK_)                                                                     \
+  do {                                                                                                                 \
+    if (replay) return launch_fast_kernel<E, T, true, true, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                    \
+    return dump ? launch_fast_kernel<E, T, true, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream)                         \
+                : launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                       \
+  } while (0)
+  if (psk) OFDM_FAST_VARIANT(false, false, false, true);       // M-ary PSK, one order
+  if (isi && sc) OFDM_FAST_VARIANT(false, true, true, false);  // SC-OFDM with a prefix shorter than the channel memory
+  if (isi) OFDM_FAST_VARIANT(false, false, true, false);       // prefix shorter than the channel memory: chained symbols
+  if (sc) OFDM_FAST_VARIANT(false, true, false, false);        // single-carrier OFDM: one order on every sample
+  if (adapt) OFDM_FAST_VARIANT(true, false, false, false);     // per-subcarrier orders / applied power loading
+#undef OFDM_FAST_VARIANT
+  if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
+  if (dump) return launch_fast_kernel<E, T, true, false>(L, p, stream);
   // One-warp teams: the warps that share a scheduler walk the code in step (named barrier per scheduler, SYNC = 2;
   // free-running warps lose ~3 % to instruction-cache misses at N = 1024, profiles/).  Multi-warp teams already meet
   // at their team barriers and lose ~5 % to an extra one (N = 4096), so they run with SYNC = 0.
-  // OFDM_B200_FAST_VARIANT=4 / =2 force SYNC = 0 / 2 for experiments.
-  static const int variant = [] { const char* v = std::getenv("OFDM_B200_FAST_VARIANT"); return v ? std::atoi(v) : 0; }();
-  const int sync = variant == 4 ? 0 : variant == 2 ? 2 : SYNC_DEFAULT;
-  return sync == 0 ? launch_fast_kernel<E, T, false, false, 512, 0>(L, p, stream)
-                   : launch_fast_kernel<E, T, false, false, 512, 2>(L, p, stream);
+  constexpr int S = T > 32 ? 0 : 2;
+#ifdef OFDM_FAST_EXPERIMENTS
+  // OFDM_B200_FAST_OPT=<bits> selects the noise / FIR formulation of the headline kernel (tools/time_fused.py sweeps)
+  static const int opt = [] { const char* v = std::getenv("OFDM_B200_FAST_OPT"); return v ? std::atoi(v) : kOptDefault; }();
+  static const int sync = [] { const char* v = std::getenv("OFDM_B200_FAST_SYNC"); return v ? std::atoi(v) : S; }();
+  if (L->d.n_taps > 4 || std::getenv("OFDM_B200_FAST_TAPS8")) {
+    if (sync != S) return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, 2 - S>(L, p, stream);
+    switch (opt) {
+      case 0: return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, 0>(L, p, stream);
+      case 1: return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, 1>(L, p, stream);
+      case 2: return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, 2>(L, p, stream);
+      default: break;
+    }
+  }
+#endif
+  if (L->d.n_taps <= 1) return launch_fast_kernel<E, T, false, false, false, false, false, false, 1>(L, p, stream);
+  if (L->d.n_taps <= 4) return launch_fast_kernel<E, T, false, false, false, false, false, false, 4>(L, p, stream);
+  return launch_fast_kernel<E, T, false, false>(L, p, stream);
 }
 
 }  // namespace ofdm

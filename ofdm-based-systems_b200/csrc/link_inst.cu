@@ -17,16 +17,8 @@ int configure_kernel(ofdm_link* L) {
   L->block = G::BLOCK;
   L->teams = G::TEAMS;
   L->smem = G::SMEM_BYTES;
-  auto kern = ofdm_link_kernel<N, E>;
-  static int occ = 0;   // per process: the attribute and the occupancy query cost ~0.1 ms each
-  if (occ == 0) {
-    if (G::SMEM_BYTES > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::BLOCK, G::SMEM_BYTES));
-    if (occ <= 0) occ = 1;
-  }
-  L->occ = occ;
-  return OFDM_OK;
+  // resident blocks per SM on the link's device (the caller has made it current); cached per (kernel, device)
+  return blocks_per_sm(ofdm_link_kernel<N, E>, G::BLOCK, G::SMEM_BYTES, &L->occ);
 }
 
 template <int N>

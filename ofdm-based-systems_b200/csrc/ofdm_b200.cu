@@ -3,7 +3,9 @@
 #include "../../include/ofdm_b200.h"
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <cmath>
 #include <complex>
 #include <cstdarg>
@@ -90,6 +92,23 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int blocks_per_sm_cached(const void* kernel, int block, size_t smem, int* out) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> cache;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({kernel, dev});
+  if (it == cache.end()) {
+    int occ = 0;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
+    it = cache.emplace(std::make_pair(kernel, dev), occ > 0 ? occ : 1).first;
+  }
+  *out = it->second;
+  return OFDM_OK;
+}
 }  // namespace ofdm
 
 namespace {
@@ -196,6 +215,8 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   const int side = 1 << half_bits;
   std::memset(&f, 0, sizeof(f));
   std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
+  for (int l = 0; l < kFastTaps; ++l)   // Gauss form of the complex product (link_fast.cuh, FIR stage)
+    f.taps3[l] = make_float4(L->taps_fast[l].x, L->taps_fast[l].y - L->taps_fast[l].x, L->taps_fast[l].x + L->taps_fast[l].y, 0.f);
   f.eq_tab = L->d_eq_fast;
   f.tw = L->d_tw_fast;
   f.field_masks = L->d_mask;
@@ -204,10 +225,11 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   f.level_tab = L->d_level;
   const double snr_lin = std::pow(10.0, snr_db / 10.0);
   // equalization/models.py:43-49 on the unscaled FFT output Y~ = sqrt(N) Y
-  f.mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f
-             : L->mean_h2 == 0.0            ? INFINITY
-                                            : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
+  f.point_tab[0].mmse_c = L->d.equalizer != OFDM_EQ_MMSE ? 0.f
+                          : L->mean_h2 == 0.0            ? INFINITY
+                                                         : (float)(1.0 / (double(N) * double(N) * snr_lin * L->mean_h2));
   f.slice_top = float(side - 1);
+  f.n_points = 1;
   const double tap_scale = L->d.modulator == OFDM_MOD_SC_OFDM ? 1.0 / L->knorm : 1.0 / (L->knorm * std::sqrt((double)N));
   f.tx_scale2 = (float)(tap_scale * tap_scale);
   f.z_unscale = (float)(2.0 * (side - 1) / L->knorm);
@@ -227,8 +249,6 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
     f.z_unscale = 1.f;
   }
   f.counters = L->d_cnt->cnt;
-  f.tx_power_sum = &L->d_cnt->power_sum;
-  f.tx_power_max_bits = &L->d_cnt->power_max_bits;
   if (dump_dev) {
     f.dump_y = reinterpret_cast<float2*>(dump_dev->y);
     f.dump_z = reinterpret_cast<float2*>(dump_dev->z);
@@ -293,10 +313,7 @@ struct DumpStage {
   }
 };
 
-int read_counters(ofdm_link* L, cudaStream_t stream, ofdm_link_result* out) {
-  CounterBlock h;
-  CUDA_TRY(cudaMemcpyAsync(&h, L->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, stream));
-  CUDA_TRY(cudaStreamSynchronize(stream));
+void to_result(const ofdm_link* L, const CounterBlock& h, ofdm_link_result* out) {
   out->bit_errors = h.cnt[CNT_BIT_ERRORS];
   out->bits = h.cnt[CNT_BITS];
   out->symbol_errors = h.cnt[CNT_SYM_ERRORS];
@@ -307,10 +324,32 @@ int read_counters(ofdm_link* L, cudaStream_t stream, ofdm_link_result* out) {
   double mx;
   std::memcpy(&mx, &h.power_max_bits, sizeof(mx));
   out->tx_power_max = mx;
+}
+
+// device block of `n_points` counter blocks for sweep launches, grown on demand
+int reserve_sweep(ofdm_link* L, int n_points) {
+  if (L->sweep_cap >= n_points) return OFDM_OK;
+  if (L->d_sweep) cudaFree(L->d_sweep);
+  L->d_sweep = nullptr;
+  L->sweep_cap = 0;
+  const int cap = n_points < 64 ? 64 : n_points;
+  CUDA_TRY(cudaMalloc(&L->d_sweep, size_t(cap) * sizeof(CounterBlock)));
+  L->sweep_cap = cap;
   return OFDM_OK;
 }
 
-__global__ void pack_counters_kernel(const CounterBlock* c, double* row, int rank, int world) {
+int read_counters(ofdm_link* L, cudaStream_t stream, ofdm_link_result* out) {
+  CounterBlock h;
+  CUDA_TRY(cudaMemcpyAsync(&h, L->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  to_result(L, h, out);
+  return OFDM_OK;
+}
+
+// one block per counter block (SNR point): row b of the all-reduce payload
+__global__ void pack_counters_kernel(const CounterBlock* blocks, double* payload, int rank, int world) {
+  const CounterBlock* c = blocks + blockIdx.x;
+  double* row = payload + (size_t)blockIdx.x * (9 + world);
   const int i = threadIdx.x;
   if (i < 8) row[i] = (double)c->cnt[i];
   else if (i == 8) row[8] = c->power_sum;
@@ -465,7 +504,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
       // and 1/(s-1) (unit interval for FFMA.SAT) folded into A; 4th component = s-1
       std::vector<float4> eqf(N);
       const int E = fast_samples_per_lane(N), T = N / E, Wd = T / E;
-      level_host.assign(N, make_float2(0.f, -8388609.0f));
+      level_host.assign(N, make_float2(0.f, -8388608.0f));
       mask_host.assign(size_t(E / 4) * T, 0u);
       bitoff_host.assign(N, 0);
       {
@@ -513,7 +552,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
           } else {
             eqf[k] = make_float4((float)(H.real() * dec), (float)(H.imag() * dec), (float)std::norm(H), top);
           }
-          level_host[k] = make_float2((float)((amp ? amp[k] : 1.0) / knorm_k), -(8388608.0f + float(side)));
+          level_host[k] = make_float2((float)((amp ? amp[k] : 1.0) / knorm_k), -(8388608.0f + float(side - 1)));
           const int t = k % T, m = k / T;
           mask_host[size_t(m / 4) * T + t] |= (unsigned)((side - 1) << 1) << (8 * (m % 4));
         }
@@ -579,6 +618,7 @@ void ofdm_link_destroy(ofdm_link* L) {
   DeviceGuard guard(L->device);
   // the cached arena may be handed to the next link at once: everything this link queued on the device must be done
   cudaDeviceSynchronize();
+  if (L->d_sweep) cudaFree(L->d_sweep);
   g_arenas.release(L->arena, L->table_bytes, L->device);
   delete L;
 }
@@ -587,6 +627,27 @@ int ofdm_link_bits_per_ofdm_symbol(const ofdm_link* L) { return L ? L->bits_per_
 int ofdm_link_uses_fast_kernel(const ofdm_link* L) { return L ? (L->fast != 0) : OFDM_EINVAL; }
 uint64_t ofdm_link_table_bytes(const ofdm_link* L) { return L ? L->table_bytes : 0; }
 void* ofdm_link_counters_device_ptr(ofdm_link* L) { return L ? (void*)L->d_cnt : nullptr; }
+
+int ofdm_link_debug_tables(const ofdm_link* L, float* eq, float* level, uint32_t* masks, float* taps, float* taps3) {
+  if (!L) return fail(OFDM_EINVAL, "null link");
+  if (!L->fast) return fail(OFDM_EUNSUPPORTED, "this link runs on the general kernel: no folded tables");
+  DeviceGuard guard(L->device);
+  const int N = L->d.n_subcarriers;
+  if (eq) CUDA_TRY(cudaMemcpy(eq, L->d_eq_fast, N * sizeof(float4), cudaMemcpyDeviceToHost));
+  if (level) {
+    if (!L->d_level) return fail(OFDM_EINVAL, "no level table: the link has one order on every subcarrier");
+    CUDA_TRY(cudaMemcpy(level, L->d_level, N * sizeof(float2), cudaMemcpyDeviceToHost));
+  }
+  if (masks) {
+    if (!L->d_mask) return fail(OFDM_EINVAL, "no field masks: the link has one order on every subcarrier");
+    CUDA_TRY(cudaMemcpy(masks, L->d_mask, (N / 4) * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  }
+  FastParams f;
+  fill_fast(L, f, 0.0, nullptr);
+  if (taps) std::memcpy(taps, f.taps, sizeof(f.taps));
+  if (taps3) std::memcpy(taps3, f.taps3, sizeof(f.taps3));
+  return OFDM_OK;
+}
 
 int ofdm_link_reset_counters(ofdm_link* L, void* stream) {
   if (!L) return fail(OFDM_EINVAL, "null link");
@@ -599,7 +660,7 @@ int ofdm_link_pack_counters(ofdm_link* L, double* payload_row_dev, int32_t rank,
   if (!L || !payload_row_dev) return fail(OFDM_EINVAL, "null argument");
   if (world < 1 || world > 1000 || rank < 0 || rank >= world) return fail(OFDM_EINVAL, "rank %d of %d", rank, world);
   DeviceGuard guard(L->device);
-  pack_counters_kernel<<<1, 9 + world + ((32 - (9 + world) % 32) % 32), 0, (cudaStream_t)stream>>>(L->d_cnt, payload_row_dev, rank, world);
+  pack_counters_kernel<<<1, (9 + world + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(L->d_cnt, payload_row_dev, rank, world);
   count_launch();
   CUDA_TRY(cudaGetLastError());
   return OFDM_OK;
@@ -620,7 +681,7 @@ int ofdm_link_launch_fused(ofdm_link* L, double snr_db, double noise_sigma, uint
     // common link shape: the fast kernel (link_fast.cuh); its Philox streams are its own
     FastParams f;
     fill_fast(L, f, snr_db, dump_dev);
-    f.sigma = (float)noise_sigma;
+    f.point_tab[0].sigma = (float)noise_sigma;
     f.seed = seed;
     f.point = point;
     f.sym_begin = first_symbol;
@@ -676,6 +737,89 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
   p.compare_limit = compare_limit_bits;
   set_dump(p, dump_dev);
   return launch(L, p, (cudaStream_t)stream);
+}
+
+int ofdm_link_launch_sweep(ofdm_link* L, int32_t n_points, const double* snr_db, const double* noise_sigma, uint64_t seed,
+                           uint32_t first_point, uint64_t first_symbol, uint64_t n_symbols, void* stream_) {
+  if (!L || !snr_db || !noise_sigma) return fail(OFDM_EINVAL, "null argument");
+  if (n_points < 1 || n_points > 65536) return fail(OFDM_EINVAL, "n_points=%d: need 1..65536", n_points);
+  if (L->bits_per_ofdm == 0) return fail(OFDM_EINVAL, "No active subcarriers (all orders are zero)");
+  DeviceGuard guard(L->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = reserve_sweep(L, n_points);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(L->d_sweep, 0, size_t(n_points) * sizeof(CounterBlock), stream));
+  L->sweep_points = n_points;
+  if (L->fast) {
+    // up to kMaxSweepPoints SNR points per launch: a point is a slice of the grid, its table rides in the parameter block
+    for (int base = 0; base < n_points; base += kMaxSweepPoints) {
+      const int k = n_points - base < kMaxSweepPoints ? n_points - base : kMaxSweepPoints;
+      FastParams f;
+      fill_fast(L, f, snr_db[base], nullptr);
+      for (int i = 0; i < k; ++i) {
+        FastParams g;
+        fill_fast(L, g, snr_db[base + i], nullptr);    // the MMSE constant of this point
+        f.point_tab[i].sigma = (float)noise_sigma[base + i];
+        f.point_tab[i].mmse_c = g.point_tab[0].mmse_c;
+      }
+      f.n_points = (unsigned)k;
+      f.counters = reinterpret_cast<unsigned long long*>(L->d_sweep + base);
+      f.seed = seed;
+      f.point = first_point + (uint32_t)base;
+      f.sym_begin = first_symbol;
+      f.sym_count = n_symbols;
+      rc = launch_fast(L, f, false, false, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, L->fast == 3, stream);
+      if (rc) return rc;
+    }
+    return OFDM_OK;
+  }
+  for (int i = 0; i < n_points; ++i) {   // general kernel: one launch per point into the point's counter block
+    LinkParams p;
+    fill_params(L, p, snr_db[i]);
+    p.bits_src = SRC_PHILOX;
+    p.noise_src = noise_sigma[i] > 0.0 ? SRC_PHILOX : SRC_NONE;
+    p.sigma = (float)noise_sigma[i];
+    p.seed = seed;
+    p.point = first_point + (uint32_t)i;
+    p.sym_begin = first_symbol;
+    p.sym_count = n_symbols;
+    p.counters = L->d_sweep[i].cnt;
+    p.tx_power_sum = &L->d_sweep[i].power_sum;
+    p.tx_power_max_bits = &L->d_sweep[i].power_max_bits;
+    rc = launch(L, p, stream);
+    if (rc) return rc;
+  }
+  return OFDM_OK;
+}
+
+int ofdm_link_read_sweep(ofdm_link* L, void* stream, int32_t n_points, ofdm_link_result* out) {
+  if (!L || !out) return fail(OFDM_EINVAL, "null argument");
+  if (n_points < 1 || n_points > L->sweep_points) return fail(OFDM_EINVAL, "n_points=%d: the last sweep launch had %d", n_points, L->sweep_points);
+  DeviceGuard guard(L->device);
+  std::vector<CounterBlock> h(n_points);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), L->d_sweep, size_t(n_points) * sizeof(CounterBlock), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int i = 0; i < n_points; ++i) to_result(L, h[i], &out[i]);
+  return OFDM_OK;
+}
+
+int ofdm_link_pack_sweep(ofdm_link* L, double* payload_dev, int32_t rank, int32_t world, void* stream) {
+  if (!L || !payload_dev) return fail(OFDM_EINVAL, "null argument");
+  if (world < 1 || world > 1000 || rank < 0 || rank >= world) return fail(OFDM_EINVAL, "rank %d of %d", rank, world);
+  if (L->sweep_points < 1) return fail(OFDM_EINVAL, "no sweep launch to pack");
+  DeviceGuard guard(L->device);
+  pack_counters_kernel<<<L->sweep_points, (9 + world + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(L->d_sweep, payload_dev, rank, world);
+  count_launch();
+  CUDA_TRY(cudaGetLastError());
+  return OFDM_OK;
+}
+
+int ofdm_link_run_sweep(ofdm_link* L, int32_t n_points, const double* snr_db, const double* noise_sigma, uint64_t seed,
+                        uint32_t first_point, uint64_t first_symbol, uint64_t n_symbols, ofdm_link_result* out) {
+  if (!L || !out) return fail(OFDM_EINVAL, "null argument");
+  int rc = ofdm_link_launch_sweep(L, n_points, snr_db, noise_sigma, seed, first_point, first_symbol, n_symbols, nullptr);
+  if (rc) return rc;
+  return ofdm_link_read_sweep(L, nullptr, n_points, out);
 }
 
 int ofdm_link_run_fused(ofdm_link* L, double snr_db, double noise_sigma, uint64_t seed, uint32_t point,

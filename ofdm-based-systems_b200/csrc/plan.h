@@ -23,11 +23,21 @@ struct CounterBlock {  // device-resident accumulator, 80 bytes
 int fail(int code, const char* fmt, ...);
 void count_launch();
 
+int blocks_per_sm_cached(const void* kernel, int block, size_t smem, int* out);
+
 #define CUDA_TRY(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t _e = (expr);                                                                             \
     if (_e != cudaSuccess) return ::ofdm::fail(OFDM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+
+// Resident blocks per SM of `kernel` on the CURRENT device, with the opt-in for more than 48 KB of dynamic shared
+// memory done on first use.  Both are per kernel and per device (the attribute lives in the device's primary context),
+// so the cache is keyed by (kernel, device ordinal); any host thread.
+template <class Kern>
+int blocks_per_sm(Kern kern, int block, size_t smem, int* out) {
+  return blocks_per_sm_cached(reinterpret_cast<const void*>(kern), block, smem, out);
+}
 
 }  // namespace ofdm
 
@@ -43,6 +53,8 @@ struct ofdm_link {
   float4* d_eq = nullptr;
   float2* d_tw = nullptr;
   ofdm::CounterBlock* d_cnt = nullptr;
+  ofdm::CounterBlock* d_sweep = nullptr;  // one counter block per SNR point of the last sweep launch (own allocation)
+  int sweep_cap = 0, sweep_points = 0;
   unsigned char* arena = nullptr;  // single device allocation behind all the pointers above
   int device = 0, sms = 0, occ = 1;
   size_t smem = 0;

@@ -62,8 +62,10 @@ EXPORTS = (
     "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_create_loaded", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
     "ofdm_link_uses_fast_kernel",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
+    "ofdm_link_run_sweep", "ofdm_link_launch_sweep", "ofdm_link_read_sweep", "ofdm_link_pack_sweep",
     "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr", "ofdm_link_pack_counters",
     "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev", "ofdm_frames_run",
+    "ofdm_link_debug_tables", "ofdm_frames_debug_tables", "ofdm_frames_header_floats",
 )
 
 
@@ -92,6 +94,10 @@ def _load() -> C.CDLL:
     lib.ofdm_link_run_replay.argtypes = [vp, dbl, vp, u64, vp, i32, u64, u64, C.POINTER(LinkDump), C.POINTER(LinkResult)]
     lib.ofdm_link_launch_fused.argtypes = [vp, dbl, dbl, u64, u32, u64, u64, C.POINTER(LinkDump), vp]
     lib.ofdm_link_launch_replay.argtypes = [vp, dbl, vp, u64, vp, i32, u64, u64, C.POINTER(LinkDump), vp]
+    lib.ofdm_link_run_sweep.argtypes = [vp, i32, vp, vp, u64, u32, u64, u64, vp]
+    lib.ofdm_link_launch_sweep.argtypes = [vp, i32, vp, vp, u64, u32, u64, u64, vp]
+    lib.ofdm_link_read_sweep.argtypes = [vp, vp, i32, vp]
+    lib.ofdm_link_pack_sweep.argtypes = [vp, vp, i32, i32, vp]
     lib.ofdm_link_reset_counters.argtypes = [vp, vp]
     lib.ofdm_link_read_result.argtypes = [vp, vp, C.POINTER(LinkResult)]
     lib.ofdm_link_counters_device_ptr.argtypes = [vp]
@@ -100,6 +106,9 @@ def _load() -> C.CDLL:
     lib.ofdm_waterfill_bitload_batched.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     lib.ofdm_waterfill_bitload_batched_dev.argtypes = [C.POINTER(WaterfillDesc), vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
     lib.ofdm_frames_run.argtypes = [C.POINTER(FramesDesc), vp, C.c_int64, u64, u64, u32, u64, C.POINTER(LinkResult), vp, vp, vp]
+    lib.ofdm_link_debug_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ofdm_frames_debug_tables.argtypes = [C.POINTER(FramesDesc), vp, C.c_int64, u64, u64, vp, vp, vp, vp]
+    lib.ofdm_frames_header_floats.restype = i32
     if lib.ofdm_b200_abi_version() != 1:
         raise NativeLibraryMissing(f"{LIB_PATH}: ABI version {lib.ofdm_b200_abi_version()} != 1, rebuild it")
     return lib
@@ -245,6 +254,39 @@ class Link:
         out = LinkCounters.from_struct(res)
         return (out, arrs) if dump else out
 
+    # ---- a whole SNR sweep in one launch (ofdm_link_run_sweep / _launch_sweep / _read_sweep / _pack_sweep)
+    @staticmethod
+    def _sweep_arrays(snr_dbs, noise_sigmas):
+        snr = np.ascontiguousarray(snr_dbs, dtype=np.float64).reshape(-1)
+        sig = np.ascontiguousarray(noise_sigmas, dtype=np.float64).reshape(-1)
+        if snr.size == 0 or snr.size != sig.size:
+            raise ValueError("a sweep needs one noise sigma per SNR point and at least one point")
+        return snr, sig
+
+    def run_sweep(self, snr_dbs, noise_sigmas, n_symbols: int, *, seed: int = 0x0FD3, first_point: int = 0,
+                  first_symbol: int = 0):
+        """Every SNR point over the same symbol range in one kernel launch; list of LinkCounters, one per point."""
+        snr, sig = self._sweep_arrays(snr_dbs, noise_sigmas)
+        res = (LinkResult * snr.size)()
+        _check(lib.ofdm_link_run_sweep(self._h, snr.size, snr.ctypes.data, sig.ctypes.data, seed, first_point,
+                                       first_symbol, n_symbols, res))
+        return [LinkCounters.from_struct(r) for r in res]
+
+    def launch_sweep(self, snr_dbs, noise_sigmas, n_symbols: int, *, seed: int = 0x0FD3, first_point: int = 0,
+                     first_symbol: int = 0, stream: int = 0) -> int:
+        snr, sig = self._sweep_arrays(snr_dbs, noise_sigmas)
+        _check(lib.ofdm_link_launch_sweep(self._h, snr.size, snr.ctypes.data, sig.ctypes.data, seed, first_point,
+                                          first_symbol, n_symbols, stream))
+        return int(snr.size)
+
+    def read_sweep(self, n_points: int, stream: int = 0):
+        res = (LinkResult * n_points)()
+        _check(lib.ofdm_link_read_sweep(self._h, stream, n_points, res))
+        return [LinkCounters.from_struct(r) for r in res]
+
+    def pack_sweep(self, payload_dev: int, rank: int, world: int, stream: int = 0) -> None:
+        _check(lib.ofdm_link_pack_sweep(self._h, payload_dev, rank, world, stream))
+
     # ---- device-pointer entry points (asynchronous on a CUDA stream handle)
     def reset_counters(self, stream: int = 0) -> None:
         _check(lib.ofdm_link_reset_counters(self._h, stream))
@@ -265,6 +307,20 @@ class Link:
 
     def pack_counters(self, payload_row_dev: int, rank: int, world: int, stream: int = 0) -> None:
         _check(lib.ofdm_link_pack_counters(self._h, payload_row_dev, rank, world, stream))
+
+    def debug_tables(self) -> dict:
+        """Test hook: the folded fp32 tables of the register-resident kernel as the device holds them."""
+        n = self.n_subcarriers
+        out = dict(eq=np.zeros((n, 4), np.float32), taps=np.zeros((8, 2), np.float32), taps3=np.zeros((8, 4), np.float32))
+        per_sc = dict(level=np.zeros((n, 2), np.float32), masks=np.zeros(n // 4, np.uint32))
+        rc = lib.ofdm_link_debug_tables(self._h, out["eq"].ctypes.data, per_sc["level"].ctypes.data,
+                                        per_sc["masks"].ctypes.data, out["taps"].ctypes.data, out["taps3"].ctypes.data)
+        if rc == 0:
+            out.update(per_sc)
+        else:   # one order on every subcarrier: no per-subcarrier level / mask tables
+            _check(lib.ofdm_link_debug_tables(self._h, out["eq"].ctypes.data, None, None, out["taps"].ctypes.data,
+                                              out["taps3"].ctypes.data))
+        return out
 
     @property
     def counters_device_ptr(self) -> int:
@@ -347,6 +403,27 @@ def run_frames(n_subcarriers: int, n_frames: int, symbols_per_frame: int, snr_db
     return dict(total=LinkCounters.from_struct(total),
                 frames=[LinkCounters.from_struct(r) for r in frames] if per_frame else None,
                 orders=None if orders is None else orders.astype(np.int64), taps=taps_out)
+
+
+def frames_debug_tables(n_subcarriers: int, taps: np.ndarray, snr_db: float, *, prefix_len: Optional[int] = None,
+                        equalizer: str = "MMSE", order: Optional[int] = None, waterfilling: bool = True,
+                        min_order: int = 4, max_order: int = 256, ser: float = 1e-3, device: int = -1) -> dict:
+    """Test hook: the per-frame fp32 tables ofdm_frames_run builds on the device for these raw taps [F, L]."""
+    require_gpu()
+    taps = np.ascontiguousarray(np.atleast_2d(taps), dtype=np.complex128)
+    f, l = taps.shape
+    n = int(n_subcarriers)
+    desc = FramesDesc(n, int(l - 1 if prefix_len is None else prefix_len), EQUALIZER[equalizer], int(l),
+                      0 if order is not None else 1, int(order or 0), int(bool(waterfilling)), int(min_order), int(max_order),
+                      int(device), float(snr_db), bit_loading_gap(ser, "QAM"))
+    hf = int(lib.ofdm_frames_header_floats())
+    out = dict(eq=np.zeros((f, n, 4), np.float32), level=np.zeros((f, n, 2), np.float32),
+               masks=np.zeros((f, n // 4), np.uint32), hdr=np.zeros((f, hf), np.float32))
+    _check(lib.ofdm_frames_debug_tables(C.byref(desc), taps.ctypes.data, f, 0, 0, out["eq"].ctypes.data,
+                                        out["level"].ctypes.data, out["masks"].ctypes.data, out["hdr"].ctypes.data))
+    out.update(taps=out["hdr"][:, :16].reshape(f, 8, 2), taps3=out["hdr"][:, 16:48].reshape(f, 8, 4),
+               sigma=out["hdr"][:, 48], mmse_c=out["hdr"][:, 49])
+    return out
 
 
 def measure_fp32_tflops(iters: int = 4096) -> float:

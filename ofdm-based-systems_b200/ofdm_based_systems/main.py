@@ -1,9 +1,9 @@
 """Batch driver: ``python -m ofdm_based_systems.main`` (reference: main.py:19-393).
 
 Same classes, file-naming contract and CSV upsert as the reference; the plots are drawn with Pillow
-(``simulation/plotting.py``) because matplotlib is not part of this image.  Every SNR point is one
-``Simulation.run()`` = one CUDA launch; for multi-GPU sweeps of one link shape use
-``ofdm_based_systems.simulation.sweep.LinkSweep`` directly."""
+(``simulation/plotting.py``) because matplotlib is not part of this image.  ``run_all`` hands the list of
+Simulations to ``Simulation.run_sweep``: the SNR values that share a link run as ONE CUDA launch, sharded over
+the ranks of an initialised ``torch.distributed`` process group with one all-reduce per sweep."""
 from __future__ import annotations
 
 import shutil
@@ -136,11 +136,11 @@ class SimulationRunner:
         print(f"\n{self.simulation_settings}\n")
         simulations = Simulation.create_from_simulation_settings(self.simulation_settings)
         print(f"Created {len(simulations)} simulation(s) to run\n")
-        results = []
-        for i, sim in enumerate(simulations, start=1):
-            print(f"\n{'#' * 80}\n  Running Simulation {i}/{len(simulations)} (SNR = {sim.snr_db} dB)\n{'#' * 80}\n")
-            result = sim.run()
-            results.append(result)
+        # the reference runs sim.run() one SNR after the other (main.py:234-240); here the SNR points that share a link
+        # are one launch, and the per-simulation report blocks are printed as the results are unpacked
+        results = Simulation.run_sweep(simulations)
+        for i, (sim, result) in enumerate(zip(simulations, results), start=1):
+            print(f"\n{'#' * 80}\n  Simulation {i}/{len(simulations)} (SNR = {sim.snr_db} dB)\n{'#' * 80}\n")
             print(f"\n  Simulation {i} completed")
             print(f"    BER: {result['bit_error_rate']:.6e}")
             print(f"    Bit Errors: {result['bit_errors']}/{result['total_bits']}")

@@ -171,6 +171,8 @@ class Simulation:
                 if bits_per_ofdm == 0:
                     raise ValueError("All subcarriers have zero order - cannot transmit data")
                 num_ofdm = self.num_bits // bits_per_ofdm
+            if num_ofdm <= 0:      # AdaptiveBitsGenerator (bits_generation/models.py:95-120) refuses an empty run
+                raise ValueError(f"num_ofdm_symbols must be positive, got {num_ofdm}")
             total_bits = bits_per_ofdm * num_ofdm
             if bits_per_ofdm == 0:
                 raise ValueError("No active subcarriers (all orders are zero)")
@@ -203,14 +205,70 @@ class Simulation:
                     bits_per_ofdm=bits_per_ofdm, adaptive=adaptive)
 
     def run(self) -> Dict[str, Any]:
+        """One SNR point (simulation/models.py:214-818).  Configuration errors surface before the device is touched."""
+        return Simulation.run_sweep([self])[0]
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _link_key(pl: Dict[str, Any]):
+        """Simulations whose plans agree on this key run on ONE configured link (they differ in SNR only)."""
+        cfg = pl["cfg"]
+        return (cfg.num_subcarriers, cfg.taps_raw.tobytes(), cfg.orders.tobytes(), cfg.constellation_scheme,
+                cfg.modulator_type, cfg.prefix_scheme, cfg.prefix_length, cfg.equalizator_type, cfg.awgn,
+                pl["num_ofdm"], pl["total_bits"], pl["adaptive"])
+
+    @staticmethod
+    def run_sweep(simulations: List["Simulation"], group=None) -> List[Dict[str, Any]]:
+        """The reference's sequential SNR loop (main.py:234-240) as sharded launches: the simulations that share a link
+        (the list ``create_from_simulation_settings`` returns in FIXED mode: one link, K SNR values) run as ONE kernel
+        launch with the SNR point as a grid dimension; with an initialised ``torch.distributed`` process group every
+        rank takes a contiguous share of the OFDM-symbol range and ONE all-reduce per sweep combines the counters.
+        Adaptive loading depends on the SNR, so those simulations are groups of one.  Results come back in input order."""
         from ofdm_based_systems import _native
+        from ofdm_based_systems.simulation.sweep import LinkSweep
+        plans = [sim.plan() for sim in simulations]          # ValueErrors of the configuration come first
         _native.require_gpu()
+        groups: Dict[Any, List[int]] = {}
+        for i, pl in enumerate(plans):
+            groups.setdefault(Simulation._link_key(pl), []).append(i)
+        results: List[Optional[Dict[str, Any]]] = [None] * len(simulations)
+        for members in groups.values():
+            pl0, sims = plans[members[0]], [simulations[i] for i in members]
+            cfg, num_ofdm, total_bits, mapper = pl0["cfg"], pl0["num_ofdm"], pl0["total_bits"], pl0["mapper"]
+            start = time.perf_counter()
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
+            sweep = LinkSweep(cfg)
+            link = sweep.link
+            try:
+                snrs = [float(sim.snr_db) for sim in sims]
+                ragged = (not pl0["adaptive"]) and total_bits != pl0["num_constellation_symbols"] * mapper.bits_per_symbol
+                sample_ofdm = max(1, min(num_ofdm, MAX_RETURNED_SAMPLES // cfg.num_subcarriers))
+                if ragged:
+                    pairs = [sim._run_ragged(link, cfg, pl0, cfg.noise_sigma(snr)) for sim, snr in zip(sims, snrs)]
+                    counters, received = [c for c, _ in pairs], [z for _, z in pairs]
+                else:
+                    # ---- the hot path: ONE launch for every SNR point of this link ...
+                    counters = sweep.sweep_counters(snrs, num_ofdm, seed=seed, group=group)
+                    # ---- ... plus a bounded dump launch per point for results["received_symbols"] / the scatter plot
+                    received = []
+                    for k, snr in enumerate(snrs):
+                        _, dump = link.run_fused(snr, cfg.noise_sigma(snr), sample_ofdm, seed=seed, point=k, dump=("z",))
+                        received.append(dump["z"].reshape(-1).astype(np.complex128))
+            finally:
+                sweep.close()
+            elapsed_ms = (time.perf_counter() - start) * 1000 / len(members)
+            for i, c, z in zip(members, counters, received):
+                results[i] = simulations[i]._report(plans[i], c, z, elapsed_ms, truncated=sample_ofdm < num_ofdm and not ragged)
+        return results  # type: ignore[return-value]
+
+    def _report(self, pl: Dict[str, Any], counters, received, elapsed_ms: float, truncated: bool) -> Dict[str, Any]:
+        """The reference's prints and its 29-key result dict (simulation/models.py:413-444, 509-524, 597-620, 796-810)
+        from the counters of one SNR point."""
+        cfg, prefix, mapper, orders = pl["cfg"], pl["prefix"], pl["mapper"], pl["orders"]
+        total_bits, water_level = pl["total_bits"], pl["water_level"]
         print("=" * 50)
         print("Starting OFDM-based System Simulation")
         print("=" * 50)
-        pl = self.plan()
-        cfg, prefix, mapper, orders = pl["cfg"], pl["prefix"], pl["mapper"], pl["orders"]
-        total_bits, num_ofdm, water_level = pl["total_bits"], pl["num_ofdm"], pl["water_level"]
         self._log("Using custom channel impulse response (%d taps)" % len(cfg.taps_raw)
                   if self.channel_impulse_response is not None else "Using default multipath channel (4 taps)")
         print(f"Using prefix length: {cfg.prefix_length}")
@@ -241,28 +299,6 @@ class Simulation:
         self._log(f"Power allocation computed: min={power.min():.6f}, max={power.max():.6f}")
         results["allocated_power"] = power.tolist()
 
-        # ---- the hot path: one CUDA launch (plus a bounded dump launch for the returned sample)
-        start = time.perf_counter()
-        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 31)
-        link = _native.Link(cfg.num_subcarriers, cfg.taps_chan, cfg.h_eq, cfg.orders, prefix_type=cfg.prefix_scheme,
-                            prefix_len=cfg.prefix_length, modulator=cfg.modulator_type, equalizer=cfg.equalizator_type,
-                            scheme=cfg.constellation_scheme)
-        try:
-            sigma = cfg.noise_sigma(self.snr_db)
-            ragged = (not pl["adaptive"]) and total_bits != pl["num_constellation_symbols"] * mapper.bits_per_symbol
-            sample_ofdm = max(1, min(num_ofdm, MAX_RETURNED_SAMPLES // self.num_subcarriers))
-            if ragged:
-                counters, received = self._run_ragged(link, cfg, pl, sigma)
-            elif sample_ofdm == num_ofdm:
-                counters, dump = link.run_fused(self.snr_db, sigma, num_ofdm, seed=seed, dump=("z",))
-                received = dump["z"].reshape(-1).astype(np.complex128)
-            else:
-                _, dump = link.run_fused(self.snr_db, sigma, sample_ofdm, seed=seed, dump=("z",))
-                received = dump["z"].reshape(-1).astype(np.complex128)
-                counters = link.run_fused(self.snr_db, sigma, num_ofdm, seed=seed)
-        finally:
-            link.close()
-
         papr_db = np.float64(counters.papr_db)
         print(f"PAPR: {papr_db:.2f} dB")
         results["papr_db"] = papr_db
@@ -279,10 +315,13 @@ class Simulation:
         print("=" * 50)
         results.update({"bit_errors": bit_errors, "symbol_errors": symbol_errors, "total_bits": total_bits,
                         "bit_error_rate": ber, "symbol_error_rate": ser, "received_symbols": received})
+        if truncated:
+            # the reference returns every equalised symbol; beyond MAX_RETURNED_SAMPLES only the first OFDM symbols are
+            # returned (and drawn) - this extra key says so, the counters above cover the whole run
+            results["received_symbols_truncated"] = True
         results["constellation_plot"] = draw_constellation_image(
             received, mapper.constellation, title=results["title"], ber=ber, snr_db=self.snr_db, papr_db=float(papr_db),
             orders=orders if pl["adaptive"] else None, num_subcarriers=self.num_subcarriers)
-        elapsed_ms = (time.perf_counter() - start) * 1000
         results["transmission_time_ms"] = elapsed_ms
         results["bitrate_mbps"] = total_bits / 1e6          # quirk Q2: not divided by time in the reference either
         print(f"Transmission time: {elapsed_ms:.2f} ms")

@@ -1,9 +1,9 @@
 """Sharded BER-vs-SNR sweeps on top of the CUDA link (libofdm_b200.so).
 
 The reference loops over SNR points strictly sequentially, one ``Simulation.run()`` each
-(main.py:234-240).  Here one ``LinkSweep`` owns one configured link per GPU; every SNR point is one
-kernel launch over this rank's contiguous share of the OFDM-symbol range, all launches are queued on
-one CUDA stream, and the per-rank counters of ALL points are combined by a single NCCL all-reduce at
+(main.py:234-240).  Here one ``LinkSweep`` owns one configured link per GPU; the WHOLE sweep is one
+kernel launch (the SNR point is the grid's second dimension) over this rank's contiguous share of the
+OFDM-symbol range, and the per-rank counters of ALL points are combined by a single NCCL all-reduce at
 the end of the sweep.  torch is used for the stream, the device tensors that hold the
 counters and ``torch.distributed``; the arithmetic is in the CUDA library.
 """
@@ -150,10 +150,11 @@ class LinkSweep:
 
     def enqueue(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
                 weak_scaling: bool = False, kernel_events=None):
-        """Queue every SNR point on the current CUDA stream - per point a counter reset (memset), the link kernel
-        and a one-block pack of the counters into the all-reduce payload - then ONE all-reduce; nothing is read
-        back.  Returns the device tensor [points, 9 + world] (float64) that ``finalize`` decodes.
-        ``kernel_events``: optional (start, end) torch CUDA events recorded around the link kernel of point 0."""
+        """Queue the whole sweep on the current CUDA stream - ONE launch of the link kernel with the SNR point as the
+        grid's second dimension (ofdm_link_launch_sweep), one launch that packs the per-point counters into the
+        all-reduce payload - then ONE all-reduce per sweep; nothing is read back.  Returns the device tensor
+        [points, 9 + world] (float64) that ``finalize`` decodes.
+        ``kernel_events``: optional (start, end) torch CUDA events recorded around the link kernel launch."""
         import torch
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized()
@@ -165,17 +166,15 @@ class LinkSweep:
             first, count = self.shard(n_symbols, rank, world)
         dev = torch.device("cuda", torch.cuda.current_device())
         stream = torch.cuda.current_stream().cuda_stream
-        payload = torch.empty((len(snr_dbs), 9 + world), dtype=torch.float64, device=dev)
-        row_bytes = payload.stride(0) * payload.element_size()
-        for i, snr in enumerate(snr_dbs):
-            self.link.reset_counters(stream)
-            if kernel_events is not None and i == 0:
-                kernel_events[0].record()
-            self.link.launch_fused(float(snr), self.cfg.noise_sigma(float(snr)), count, seed=seed, point=i,
-                                   first_symbol=first, stream=stream)
-            if kernel_events is not None and i == 0:
-                kernel_events[1].record()
-            self.link.pack_counters(payload.data_ptr() + i * row_bytes, rank, world, stream)
+        snrs = [float(x) for x in snr_dbs]
+        payload = torch.empty((len(snrs), 9 + world), dtype=torch.float64, device=dev)
+        if kernel_events is not None:
+            kernel_events[0].record()
+        self.link.launch_sweep(snrs, [self.cfg.noise_sigma(x) for x in snrs], count, seed=seed, first_symbol=first,
+                               stream=stream)
+        if kernel_events is not None:
+            kernel_events[1].record()
+        self.link.pack_sweep(payload.data_ptr(), rank, world, stream)
         if world > 1:
             dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group if distributed else None)
         return payload
@@ -185,25 +184,85 @@ class LinkSweep:
         (bit_errors / total_bits / bit_error_rate / symbol_errors / symbol_error_rate / papr_db)."""
         return decode_counters(snr_dbs, payload, self.cfg.num_subcarriers + self.cfg.prefix_length)
 
-    def sweep(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
-              weak_scaling: bool = False) -> List[dict]:
-        """``n_symbols`` is the global OFDM-symbol count per point (the per-rank count with
-        ``weak_scaling``); the symbol range is sharded over the ranks of the process group."""
+    def sweep_counters(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
+                       weak_scaling: bool = False) -> List[_native.LinkCounters]:
+        """The sweep as LinkCounters per point (summed over the ranks of the process group, if there is one)."""
         import torch.distributed as dist
+        snrs = [float(x) for x in snr_dbs]
         if not (dist.is_available() and dist.is_initialized()):
-            # one GPU: the plain synchronous C-ABI call per point (reset, launch, counters D2H), no torch in the loop
-            spo = self.cfg.num_subcarriers + self.cfg.prefix_length
-            out = []
-            for i, snr in enumerate(snr_dbs):
-                r = self.link.run_fused(float(snr), self.cfg.noise_sigma(float(snr)), n_symbols, seed=seed, point=i)
-                mean_p = r.tx_power_sum / max(r.ofdm_symbols * spo, 1)
-                out.append(dict(snr_db=float(snr), bit_errors=r.bit_errors, total_bits=r.bits, symbol_errors=r.symbol_errors,
-                                num_constellation_symbols=r.symbols, num_ofdm_symbols=r.ofdm_symbols,
-                                bit_error_rate=r.bit_errors / r.bits if r.bits else 0.0,
-                                symbol_error_rate=r.symbol_errors / r.symbols if r.symbols else 0.0,
-                                papr_db=float(10 * np.log10(r.tx_power_max / mean_p)) if mean_p > 0 else float("inf")))
-            return out
-        return self.finalize(snr_dbs, self.enqueue(snr_dbs, n_symbols, seed=seed, group=group, weak_scaling=weak_scaling))
+            # one GPU: the synchronous C-ABI call (counter reset, ONE launch, counters D2H), no torch in the loop
+            return self.link.run_sweep(snrs, [self.cfg.noise_sigma(x) for x in snrs], n_symbols, seed=seed)
+        host = self.enqueue(snrs, n_symbols, seed=seed, group=group, weak_scaling=weak_scaling).cpu().numpy()
+        spo = self.cfg.num_subcarriers + self.cfg.prefix_length
+        return [_native.LinkCounters(int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[4]) * spo, float(c[8]),
+                                     float(c[9:].max())) for c in host]
+
+    def sweep(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
+              weak_scaling: bool = False, ci_blocks: int = 0) -> List[dict]:
+        """``n_symbols`` is the global OFDM-symbol count per point (the per-rank count with
+        ``weak_scaling``); the symbol range is sharded over the ranks of the process group.
+
+        ``ci_blocks`` = B > 1 additionally runs the range as B contiguous blocks of OFDM symbols (B launches, each
+        sharded like the whole range, still ONE all-reduce) and adds a confidence interval from the block-to-block
+        spread of the BER - errors inside an OFDM symbol are correlated through the channel and the equaliser, so the
+        block is the unit, as in the reference-side intervals of tests/test_simulation_gpu.py: keys ``ber_sem``
+        (standard error of the mean) and ``ber_ci95`` (mean -+ 1.96 s.e.m.)."""
+        if ci_blocks and ci_blocks > 1:
+            return self._sweep_blocks(snr_dbs, n_symbols, seed, group, weak_scaling, int(ci_blocks))
+        return [self._result(snr, r) for snr, r in
+                zip(snr_dbs, self.sweep_counters(snr_dbs, n_symbols, seed=seed, group=group, weak_scaling=weak_scaling))]
+
+    @staticmethod
+    def _result(snr, r) -> dict:
+        return dict(snr_db=float(snr), bit_errors=r.bit_errors, total_bits=r.bits, symbol_errors=r.symbol_errors,
+                    num_constellation_symbols=r.symbols, num_ofdm_symbols=r.ofdm_symbols,
+                    bit_error_rate=r.bit_errors / r.bits if r.bits else 0.0,
+                    symbol_error_rate=r.symbol_errors / r.symbols if r.symbols else 0.0, papr_db=r.papr_db)
+
+    def _sweep_blocks(self, snr_dbs, n_symbols, seed, group, weak_scaling, blocks) -> List[dict]:
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank(group) if distributed else 0
+        world = dist.get_world_size(group) if distributed else 1
+        snrs = [float(x) for x in snr_dbs]
+        sig = [self.cfg.noise_sigma(x) for x in snrs]
+        total = n_symbols * world if weak_scaling else n_symbols
+        blocks = max(2, min(blocks, total))
+        edges = [total * b // blocks for b in range(blocks + 1)]
+        spo = self.cfg.num_subcarriers + self.cfg.prefix_length
+        if not distributed:
+            per_block = [self.link.run_sweep(snrs, sig, edges[b + 1] - edges[b], seed=seed, first_symbol=edges[b])
+                         for b in range(blocks)]
+        else:
+            import torch
+            dev = torch.device("cuda", torch.cuda.current_device())
+            stream = torch.cuda.current_stream().cuda_stream
+            payload = torch.zeros((blocks, len(snrs), 9 + world), dtype=torch.float64, device=dev)
+            for b in range(blocks):
+                first, count = self.shard(edges[b + 1] - edges[b], rank, world)
+                if count == 0:
+                    continue
+                self.link.launch_sweep(snrs, sig, count, seed=seed, first_symbol=edges[b] + first, stream=stream)
+                self.link.pack_sweep(payload[b].data_ptr(), rank, world, stream)
+            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+            host = payload.cpu().numpy()
+            per_block = [[_native.LinkCounters(int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[4]) * spo,
+                                               float(c[8]), float(c[9:].max())) for c in host[b]] for b in range(blocks)]
+        out = []
+        for k, snr in enumerate(snrs):
+            rows = [per_block[b][k] for b in range(blocks)]
+            tot = _native.LinkCounters(sum(r.bit_errors for r in rows), sum(r.bits for r in rows),
+                                       sum(r.symbol_errors for r in rows), sum(r.symbols for r in rows),
+                                       sum(r.ofdm_symbols for r in rows), sum(r.tx_samples for r in rows),
+                                       sum(r.tx_power_sum for r in rows), max(r.tx_power_max for r in rows))
+            res = self._result(snr, tot)
+            ber = np.array([r.bit_errors / r.bits for r in rows if r.bits])
+            # blocks have (almost) equal sizes: the unweighted spread of their BERs estimates the variance of a block mean
+            sem = float(ber.std(ddof=1) / np.sqrt(len(ber))) if len(ber) > 1 else float("nan")
+            res.update(ber_sem=sem, ber_ci95=(res["bit_error_rate"] - 1.96 * sem, res["bit_error_rate"] + 1.96 * sem),
+                       ci_blocks=len(ber))
+            out.append(res)
+        return out
 
 
 class FrameSweep:

@@ -305,6 +305,7 @@ def main():
     link_case("adaptive_psk_n64_zf", 64, 0, "PSK", ch["two_ray"], "CYCLIC", 1, "ZF", 18.0, 24, 34, orders=orders)
 
     loaded_cases(ch)
+    ber_study(ch)
 
     # Simulation.run() itself
     common = dict(num_subcarriers=64, snr_db=18.0)
@@ -324,6 +325,49 @@ def main():
              equalizator_type=EqualizationMethod.NONE, num_subcarriers=64, snr_db=30.0)
 
 
+def ber_study(ch):
+    """BER statistics of the LIVE reference with its OWN random generators, per OFDM symbol, so that the GPU's
+    independent-RNG BER can be placed inside the reference's confidence intervals (north_star):
+      * the headline link (N=1024, 64-QAM, MMSE, severe_multipath, CP=7) at 8 SNR points, 400 OFDM symbols each;
+      * the short-prefix study of docs/OFDM-Based Systems.tex:226-264 as the CURRENT code runs it:
+        Lin-Phoong P2, N=64, 64-QAM, 30 dB, {ZF, MMSE} x {CP, ZP} x prefix ratio {0.34, 0.68, 1.00, 1.34}, 1600 OFDM
+        symbols (614 400 bits) per entry."""
+    def errors_per_symbol(n_sc, order, taps, prefix_type, prefix_len, eq, snr_db, n_ofdm, seed):
+        np.random.seed(seed)
+        gen = Generator(PCG64(seed))
+        channel = ChannelModel(impulse_response=np.asarray(taps, dtype=np.complex128), snr_db=snr_db, noise_model=AWGNoiseModel())
+        prefix = PREFIX[prefix_type](prefix_length=prefix_len)
+        equalizer = EQ[eq](channel_frequency_response=np.fft.fft(taps, n_sc), snr_db=snr_db)
+        mod = OFDMModulator(num_subcarriers=n_sc, prefix_scheme=prefix, equalizator=equalizer)
+        s2p = SerialToParallelConverter()
+        mapper = QAMConstellationMapper(order=order)
+        bps = mapper.bits_per_symbol
+        with contextlib.redirect_stdout(io.StringIO()):
+            bits = RandomBitsGenerator(generator=gen).generate_bits(n_ofdm * n_sc * bps)
+            tx_bits = np.array(read_bits_from_stream(bits), dtype=np.uint8)
+            tx = s2p.to_serial(mod.modulate(s2p.to_parallel(mapper.encode(bits), n_sc)))
+            rx = s2p.to_parallel(channel.transmit(tx), n_sc + prefix.prefix_length)
+            rx_bits = np.array(read_bits_from_stream(mapper.decode(s2p.to_serial(mod.demodulate(rx)))), dtype=np.uint8)
+        return np.sum((tx_bits != rx_bits).reshape(n_ofdm, n_sc * bps), axis=1).astype(np.int32)
+
+    head_snrs = np.array([0.0, 4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0])
+    head = np.stack([errors_per_symbol(1024, 64, ch["severe_multipath"], "CYCLIC", 7, "MMSE", snr, 400, 700 + i)
+                     for i, snr in enumerate(head_snrs)])
+    ratios = np.array([0.34, 0.68, 1.00, 1.34])
+    taps = ch["Lin-Phoong_P2"]
+    sp = np.zeros((2, 2, 4, 1600), dtype=np.int32)
+    for a, eq in enumerate(("ZF", "MMSE")):
+        for b, pre in enumerate(("CYCLIC", "ZERO")):
+            for c, ratio in enumerate(ratios):
+                sp[a, b, c] = errors_per_symbol(64, 64, taps, pre, int(ratio * (len(taps) - 1)), eq, 30.0, 1600, 800 + 16 * a + 4 * b + c)
+    path = os.path.join(OUT, "ber_reference.npz")
+    np.savez_compressed(path, headline_snrs=head_snrs, headline_errors=head, headline_bits_per_symbol=1024 * 6,
+                        sp_eq=np.array(["ZF", "MMSE"]), sp_prefix=np.array(["CYCLIC", "ZERO"]), sp_ratio=ratios,
+                        sp_errors=sp, sp_bits_per_symbol=64 * 6, sp_snr_db=30.0)
+    print("headline BER:", np.round(head.sum(axis=1) / (400 * 6144), 5))
+    print("short-prefix BER (ZF/MMSE x CP/ZP x ratio):\n", np.round(sp.sum(axis=3) / (1600 * 384), 4))
+
+
 def loaded_cases(ch):
     """Applied power loading: the reference's WaterfillingPowerAllocation feeds tx amplitudes sqrt(P_k)
     and receiver gains 1/sqrt(P_k) around the reference's own mapper / modulator / channel / decoder."""
@@ -340,7 +384,11 @@ def loaded_cases(ch):
 
 
 if __name__ == "__main__":
-    if "--loaded-only" in sys.argv:
+    if "--ber-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        names = ["Lin-Phoong_P2", "severe_multipath"]
+        ber_study({n: np.load(os.path.join(CHAN, n + ".npy")) for n in names})
+    elif "--loaded-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         names = ["Lin-Phoong_P1", "Lin-Phoong_P2", "default_multipath", "flat_fading", "rayleigh_fading", "severe_multipath", "two_ray"]
         loaded_cases({n: np.load(os.path.join(CHAN, n + ".npy")) for n in names})

@@ -109,20 +109,88 @@ VARIANTS = [
     ("psk", 1024, 8, "PSK", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),
     ("adaptive", 1024, 0, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", "OFDM", True),
     ("general", 8192, 16, "QAM", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),
+    # the headline shape's short-channel instantiations (1 and 4 evaluated taps) and the small transforms of the shipped configs
+    ("flat", 64, 16, "QAM", "flat_fading", "CYCLIC", 16, "ZF", "OFDM", False),
+    ("four_taps", 64, 64, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "OFDM", False),
+    ("four_taps_256", 256, 16, "QAM", "default_multipath", "CYCLIC", 3, "ZF", "OFDM", False),
+    ("sc_isi", 512, 16, "QAM", "severe_multipath", "CYCLIC", 3, "MMSE", "SC-OFDM", False),
 ]
+
+
+def variant_link(v, kat):
+    from ofdm_based_systems._native import Link
+    name, n, order, scheme, chan, prefix, P, eq, modulator, adaptive = v
+    taps = kat["chan_" + chan]
+    tn = oc.normalize_taps(taps)
+    orders = np.random.default_rng(1).choice([0, 4, 16, 64, 256], size=n) if adaptive else np.full(n, order)
+    return Link(n, tn, np.fft.fft(taps, n), orders, prefix_type=prefix, prefix_len=P, equalizer=eq, modulator=modulator,
+                scheme=scheme)
+
+
+@pytest.mark.parametrize("v", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_counter_only_kernel_equals_the_dump_kernel(v, kat):
+    """The instantiation bench.py times (DUMP = false, for short channels also fewer evaluated taps) is a different
+    compilation of the same source than the one the oracle comparisons run (DUMP = true).  Same seed, same symbol range:
+    every counter - bit errors, symbol errors, power sum, power maximum - must be IDENTICAL, which pins the benchmarked
+    kernels to the oracle through tests/test_link_fused_gpu.py (simulation/models.py:597-606)."""
+    link = variant_link(v, kat)
+    n = v[1]
+    S = max(64, 400_000 // n)
+    for seed, first in ((8, 0), (0x0FD3, 12_345)):
+        plain = link.run_fused(17.0, 0.09, S, seed=seed, point=2, first_symbol=first)
+        dumped, _ = link.run_fused(17.0, 0.09, S, seed=seed, point=2, first_symbol=first, dump=("z",))
+        assert same_counters(plain, dumped) and plain.bit_errors > 0
+    link.close()
+
+
+def same_counters(a, b) -> bool:
+    """Every integer counter and the power maximum identical; the power SUM is a double accumulated by atomics in
+    launch-dependent order, so it agrees to rounding only."""
+    ints = ("bit_errors", "bits", "symbol_errors", "symbols", "ofdm_symbols", "tx_samples", "tx_power_max")
+    return all(getattr(a, k) == getattr(b, k) for k in ints) and abs(a.tx_power_sum - b.tx_power_sum) <= 1e-12 * abs(a.tx_power_sum)
+
+
+@pytest.mark.parametrize("v", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_sweep_launch_equals_per_point_launches(v, kat):
+    """ofdm_link_run_sweep (ONE launch, the SNR point is the grid's second dimension; main.py:234-240 as a single call)
+    returns, for point i, exactly the counters of ofdm_link_run_fused(point = first_point + i) over the same symbols."""
+    link = variant_link(v, kat)
+    n = v[1]
+    S = max(48, 200_000 // n)
+    snrs = [6.0, 12.0, 18.0, 24.0, 30.0]
+    sigmas = [0.30, 0.20, 0.12, 0.07, 0.04]
+    swept = link.run_sweep(snrs, sigmas, S, seed=77, first_point=3, first_symbol=1000)
+    assert len(swept) == 5
+    for i, got in enumerate(swept):
+        single = link.run_fused(snrs[i], sigmas[i], S, seed=77, point=3 + i, first_symbol=1000)
+        assert same_counters(got, single), (i, got, single)
+    assert swept[0].bit_errors > swept[-1].bit_errors
+    link.close()
+
+
+def test_sweep_of_more_points_than_one_launch_carries(kat):
+    """40 SNR points: queued as launches of 32 + 8 points into one block of counters; empty and invalid sweeps."""
+    link = headline_link(order=16, n=256)
+    snrs = list(np.linspace(0.0, 39.0, 40))
+    sigmas = [float(np.sqrt(10 ** (-x / 10) / 2)) for x in snrs]
+    swept = link.run_sweep(snrs, sigmas, 400, seed=5)
+    for i in (0, 31, 32, 39):
+        assert same_counters(swept[i], link.run_fused(snrs[i], sigmas[i], 400, seed=5, point=i))
+    empty = link.run_sweep(snrs[:3], sigmas[:3], 0)
+    assert all(r.bits == 0 and r.bit_errors == 0 for r in empty)
+    with pytest.raises(ValueError):
+        link.run_sweep([], [], 10)
+    with pytest.raises(ValueError):
+        link.run_sweep([1.0, 2.0], [0.1], 10)
+    link.close()
 
 
 @pytest.mark.parametrize("v", VARIANTS, ids=[v[0] for v in VARIANTS])
 def test_every_variant_is_deterministic_and_additive(v, kat):
     """Same seed -> identical counters run to run (a shared-memory race or an uninitialised read would show up here), and
     the counters of [0, S) equal the sum over a split of the symbol range for every kernel variant."""
-    from ofdm_based_systems._native import Link
-    name, n, order, scheme, chan, prefix, P, eq, modulator, adaptive = v
-    taps = kat["chan_" + chan]
-    tn = oc.normalize_taps(taps)
-    orders = np.random.default_rng(1).choice([0, 4, 16, 64, 256], size=n) if adaptive else np.full(n, order)
-    link = Link(n, tn, np.fft.fft(taps, n), orders, prefix_type=prefix, prefix_len=P, equalizer=eq, modulator=modulator,
-                scheme=scheme)
+    name, n = v[0], v[1]
+    link = variant_link(v, kat)
     assert link.uses_fast_kernel == (name != "general")
     S = max(300, 2_000_000 // n)
     runs = [link.run_fused(16.0, 0.11, S, seed=8, point=1, first_symbol=77) for _ in range(3)]
