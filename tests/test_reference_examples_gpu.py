@@ -20,7 +20,9 @@ CASES = [
     ("test_new_naming.py", "Test completed successfully", ["results/ber_results.csv", "images/severe_multipath"]),
     ("test_new_naming2.py", "Generated Files in images/severe_multipath", ["results/ber_results.csv", "images/severe_multipath"]),
     ("configurable_simulation_demo.py", "", []),
-    ("custom_channel_demo.py", "", []),
+    # its second half loads simulation_settings_custom_channel.json (num_symbols = 100000, not a multiple of 64): the live
+    # reference raises this ValueError from to_parallel and the script prints it with a traceback - same behaviour here
+    ("custom_channel_demo.py", "Error: Length of data must be divisible by number of streams.", []),
     ("quick_start_adaptive.py", "", []),
 ]
 
@@ -36,7 +38,8 @@ def test_reference_example_runs_unchanged(script, expect, files, tmp_path):
     run = subprocess.run([sys.executable, path], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     tail = (run.stdout[-3000:] + "\n" + run.stderr[-3000:])
     assert run.returncode == 0, tail
-    assert "Traceback" not in run.stderr, tail
+    if not expect.startswith("Error:"):
+        assert "Traceback" not in run.stderr, tail
     assert expect in run.stdout, tail
     for f in files:
         assert (tmp_path / f).exists(), (f, tail)
