@@ -16,7 +16,7 @@ int launch_frames_shape(int sms, const FastParams& p, cudaStream_t stream);
 // frame batches (frames.cu): one block per (frame, chunk of symbols) unit, grid-stride over the units
 template <>
 int launch_frames_shape<OFDM_FAST_E, OFDM_FAST_T>(int sms, const FastParams& p0, cudaStream_t stream) {
-  constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T, BLOCK = 512, SYNC = T > 32 ? 0 : 2;
+  constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T, BLOCK = 512, SYNC = 0;
   using G = FastGeometry<E, T, BLOCK>;
   auto kern = ofdm_link_fast_kernel<E, T, false, true, false, BLOCK, SYNC, true, true>;
   int occ = 1;
@@ -43,7 +43,7 @@ int launch_frames_shape<OFDM_FAST_E, OFDM_FAST_T>(int sms, const FastParams& p0,
 }
 
 template <int E, int T, bool DUMP, bool REPLAY, bool ADAPT = false, bool SC = false, bool ISI = false, bool PSK = false,
-          int TAPS = kFastTaps, int SYNC = (T > 32 ? 0 : 2), int OPT = kOptDefault>
+          int TAPS = kFastTaps, int SYNC = 0, int OPT = kOptDefault>
 static int launch_fast_kernel(const ofdm_link* L, const FastParams& p0, cudaStream_t stream) {
   constexpr int BLOCK = 512;
   using G = FastGeometry<E, T, BLOCK>;
@@ -99,10 +99,12 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
 #undef OFDM_FAST_VARIANT
   if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
   if (dump) return launch_fast_kernel<E, T, true, false>(L, p, stream);
-  // One-warp teams: the warps that share a scheduler walk the code in step (named barrier per scheduler, SYNC = 2;
-  // free-running warps lose ~3 % to instruction-cache misses at N = 1024, profiles/).  Multi-warp teams already meet
-  // at their team barriers and lose ~5 % to an extra one (N = 4096), so they run with SYNC = 0.
-  constexpr int S = T > 32 ? 0 : 2;
+  // The warps of a block run free (SYNC = 0).  Round 1 aligned the warps that share a scheduler at the section
+  // boundaries (named barrier per scheduler, SYNC = 2): they then share instruction fetches (stall_no_instruction 0.16
+  // instead of 0.49 per issue) but meet the shared-memory exchanges and the MUFU section together.  With the round-2
+  // instruction stream (two Philox calls per 8 noise samples, Gauss-form FIR) free-running warps are faster on every
+  // one-warp team shape: -3 % time at N = 1024, -10 % at N = 256, -14 % at N = 64 (profiles/r2_fast_kernel_history.md).
+  constexpr int S = 0;
 #ifdef OFDM_FAST_EXPERIMENTS
   // OFDM_B200_FAST_OPT=<bits> selects the noise / FIR formulation of the headline kernel (tools/time_fused.py sweeps)
   static const int opt = [] { const char* v = std::getenv("OFDM_B200_FAST_OPT"); return v ? std::atoi(v) : kOptDefault; }();

@@ -328,7 +328,7 @@ def main():
 def ber_study(ch):
     """BER statistics of the LIVE reference with its OWN random generators, per OFDM symbol, so that the GPU's
     independent-RNG BER can be placed inside the reference's confidence intervals (north_star):
-      * the headline link (N=1024, 64-QAM, MMSE, severe_multipath, CP=7) at 8 SNR points, 400 OFDM symbols each;
+      * the headline link (N=1024, 64-QAM, MMSE, severe_multipath, CP=7) at 8 SNR points, 1600 OFDM symbols (9.8e6 bits) each;
       * the short-prefix study of docs/OFDM-Based Systems.tex:226-264 as the CURRENT code runs it:
         Lin-Phoong P2, N=64, 64-QAM, 30 dB, {ZF, MMSE} x {CP, ZP} x prefix ratio {0.34, 0.68, 1.00, 1.34}, 1600 OFDM
         symbols (614 400 bits) per entry."""
@@ -351,8 +351,9 @@ def ber_study(ch):
         return np.sum((tx_bits != rx_bits).reshape(n_ofdm, n_sc * bps), axis=1).astype(np.int32)
 
     head_snrs = np.array([0.0, 4.0, 8.0, 12.0, 16.0, 20.0, 24.0, 28.0])
-    head = np.stack([errors_per_symbol(1024, 64, ch["severe_multipath"], "CYCLIC", 7, "MMSE", snr, 400, 700 + i)
-                     for i, snr in enumerate(head_snrs)])
+    # 4 x 400 OFDM symbols per point (the reference's nearest-neighbour classifier holds n x M complex128: 400 symbols at a time)
+    head = np.stack([np.concatenate([errors_per_symbol(1024, 64, ch["severe_multipath"], "CYCLIC", 7, "MMSE", snr, 400, 700 + i + 100 * r)
+                                     for r in range(4)]) for i, snr in enumerate(head_snrs)])
     ratios = np.array([0.34, 0.68, 1.00, 1.34])
     taps = ch["Lin-Phoong_P2"]
     sp = np.zeros((2, 2, 4, 1600), dtype=np.int32)
@@ -364,7 +365,7 @@ def ber_study(ch):
     np.savez_compressed(path, headline_snrs=head_snrs, headline_errors=head, headline_bits_per_symbol=1024 * 6,
                         sp_eq=np.array(["ZF", "MMSE"]), sp_prefix=np.array(["CYCLIC", "ZERO"]), sp_ratio=ratios,
                         sp_errors=sp, sp_bits_per_symbol=64 * 6, sp_snr_db=30.0)
-    print("headline BER:", np.round(head.sum(axis=1) / (400 * 6144), 5))
+    print("headline BER:", np.round(head.sum(axis=1) / (head.shape[1] * 6144), 5))
     print("short-prefix BER (ZF/MMSE x CP/ZP x ratio):\n", np.round(sp.sum(axis=3) / (1600 * 384), 4))
 
 

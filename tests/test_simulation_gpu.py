@@ -203,7 +203,7 @@ def family_z(n_points: int) -> float:
 def test_headline_ber_curve_inside_reference_confidence_intervals(kat):
     """north_star: independent-RNG BER curves must lie inside the reference's 95 % confidence intervals.  Reference side:
     tests/golden/ber_reference.npz, recorded by oracle/make_golden.py from the LIVE reference with its own generators
-    (PCG64 bits, MT19937 noise): bit errors per OFDM symbol, 400 OFDM symbols (2.46e6 bits) per SNR point of the headline
+    (PCG64 bits, MT19937 noise): bit errors per OFDM symbol, 1600 OFDM symbols (9.8e6 bits) per SNR point of the headline
     link -> mean and standard error with the OFDM symbol as the unit (errors inside a symbol are correlated).  GPU side:
     1.2e8 bits per point, its own sampling error (block spread, ci_blocks) added in quadrature.  The 8 intervals are
     95 % jointly (z = 2.73)."""

@@ -100,17 +100,27 @@ struct FastParams {
   int noise_f64;
 };
 
-template <int E, int T_ = E, int BLOCK_ = 512>
+// OPT bits (measured one by one on the headline shape, profiles/r2_fast_kernel_history.md):
+//   1  noise from 32 bits per complex sample (2 Philox calls per 8 samples + rare refill) instead of 48 (3 calls)
+//   2  FIR with three real products per complex tap (Gauss) instead of four
+//   4  rolled slicer: the equaliser / slicer / error count runs as a loop over the lane's label words (4 subcarriers
+//      each) on the spectrum parked in the lane's own row of shared memory, with the transmitted label words parked
+//      there since the mapper - 9 KB less code in the symbol loop (instruction cache), 16 registers less across the
+//      transforms and the channel, ~80 more instructions per OFDM symbol
+//   8  noise direction (cos, sin) from a 2048-entry table in shared memory instead of two MUFU evaluations
+//  16  PAPR maximum with three-input integer maxima on the bit patterns of |x|^2 (non-negative floats order like
+//      unsigned integers)
+constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptRollSlicer = 4, kOptTrigTable = 8, kOptMax3 = 16, kOptDefault = 3;
+constexpr int kTrigEntries = 2048;
+
+template <int E, int T_ = E, int BLOCK_ = 512, int OPT = kOptDefault>
 struct FastGeometry {
   static_assert(T_ % E == 0 && (T_ / E == 1 || T_ / E == 2 || T_ / E == 4) && (T_ <= 32 || T_ % 32 == 0), "team shape");
   static constexpr int T = T_;                // lanes per OFDM symbol
   static constexpr int N = E * T;
   static constexpr int W = T / E;             // radix of the third pass (1: two-pass transform)
   static constexpr int RS = E + 2;            // row stride (complex): conflict-free 128-bit row accesses
-  // float2 per team: T rows of E samples; teams narrower than a half-warp are offset by half a bank cycle (64 B) so that
-  // the 64-bit column accesses of the two teams of a half-warp fall on different banks (ncu: 2-way conflicts on every
-  // column access at N = 64 without the offset, profiles/r2_small_n.md)
-  static constexpr int TEAM_F2 = T * RS + ((T < 16 && (T * RS) % 16 == 0) ? 8 : 0);
+  static constexpr int TEAM_F2 = T * RS;      // float2 per team: T rows of E samples
   static constexpr int BLOCK = BLOCK_;
   static constexpr int TEAMS = BLOCK / T;
   static constexpr int TW2_F2 = E * RS;       // pass-2 twiddles (float2): one padded row per lane column, read as 128-bit pairs
@@ -119,8 +129,11 @@ struct FastGeometry {
   static constexpr int RED_F = T > 32 ? TEAMS * (T / 32) : 0;   // cross-warp reduction scratch (floats)
   static constexpr int TAIL_F2 = 8;           // ISI: last tx samples of the previous OFDM symbol, per team
   static constexpr int PSK_F2 = 256;          // PSK: point table
-  static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) +
+  static constexpr size_t BASE_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) +
                                        RED_F * sizeof(float) + (size_t(TEAMS) * TAIL_F2 + PSK_F2) * sizeof(float2);
+  static constexpr size_t TRIG_BYTES = (OPT & kOptTrigTable) ? kTrigEntries * sizeof(float2) : 0;
+  static constexpr size_t STASH_BYTES = (OPT & kOptRollSlicer) ? size_t(BLOCK) * (E / 2) * sizeof(unsigned) : 0;   // 2 * E/4 words per lane
+  static constexpr size_t SMEM_BYTES = BASE_BYTES + TRIG_BYTES + STASH_BYTES;
 };
 
 // barrier among the lanes of one team: the warp when the team fits one, else a named barrier (ids 5..12)
@@ -188,27 +201,40 @@ __device__ __forceinline__ float2 fast_noise(uint32_t wr, uint32_t wa, uint32_t 
 //   continues to u = 2^-53 (8.6 sigma) like a generator with a 52-bit radius word.
 //   angle = 2 pi (a + 0.5) / 4096 - pi via the mantissa of 2^23 + a: 4096 equally spaced rays are invisible after any
 //   projection (the radius is continuous) and noise is rotation invariant.
-constexpr uint32_t kRefillBelow = 4096u;   // w < 4096  <=>  radius field == 0
+// TRIG: the direction comes from a table in shared memory indexed by bits 3..13 (the byte offset of a float2 entry is
+//   w & 0x3FF8), the radius field is the top 18 bits and the refill continues the tail after u < 2^-18.
+template <bool TRIG> struct NoiseWord {
+  static constexpr uint32_t kLowMask = TRIG ? 0x3FFFu : 0xFFFu;   // bits below the radius field
+  static constexpr uint32_t kRefillBelow = kLowMask + 1u;          // w < kRefillBelow  <=>  radius field == 0
+  static constexpr float kFieldBits = TRIG ? 18.0f : 20.0f;
+};
+template <bool TRIG>
 __device__ __forceinline__ float noise20_radius(uint32_t w, float c2, float c2m) {
-  return fast_sqrt(fmaf(c2, fast_lg2((float)(w | 0xFFFu)), c2m));
+  return fast_sqrt(fmaf(c2, fast_lg2((float)(w | NoiseWord<TRIG>::kLowMask)), c2m));
 }
-__device__ __forceinline__ float2 noise20_dir(uint32_t w) {
-  const float f = __uint_as_float((w & 0xFFFu) | 0x4B000000u);                                   // 2^23 + a
-  const float ang = fmaf(f, 1.5339807878856412e-03f, -12871.104692850697f);                      // (2 pi / 4096)(a + 0.5) - pi (offset for the ROUNDED slope)
-  return make_float2(__cosf(ang), __sinf(ang));
+template <bool TRIG>
+__device__ __forceinline__ float2 noise20_dir(uint32_t w, const char* s_trig) {
+  if constexpr (TRIG) {
+    return *reinterpret_cast<const float2*>(s_trig + (w & 0x3FF8u));
+  } else {
+    const float f = __uint_as_float((w & 0xFFFu) | 0x4B000000u);                                   // 2^23 + a
+    const float ang = fmaf(f, 1.5339807878856412e-03f, -12871.104692850697f);                      // (2 pi / 4096)(a + 0.5) - pi (offset for the ROUNDED slope)
+    return make_float2(__cosf(ang), __sinf(ang));
+  }
 }
-__device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m) {
-  const float rad = noise20_radius(w, c2, c2m);
-  const float2 d = noise20_dir(w);
+template <bool TRIG>
+__device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m, const char* s_trig) {
+  const float rad = noise20_radius<TRIG>(w, c2, c2m);
+  const float2 d = noise20_dir<TRIG>(w, s_trig);
   return make_float2(rad * d.x, rad * d.y);
 }
 
 // Rare path of the 32-bit-per-sample noise: at least one of this lane's E radius fields was 0.  Regenerates the lane's
-// words, and for every sample with a zero field draws 32 fresh bits r: u = (r + 0.5) 2^-52, same direction; the FIR
-// output in `row` already holds the coarse sample, so the difference is added.
-template <int E, int NROUNDS>
+// words, and for every sample with a zero field draws 32 fresh bits r: u = (r + 0.5) 2^-(32 + field bits), same
+// direction; the FIR output in `row` already holds the coarse sample, so the difference is added.
+template <int E, int NROUNDS, bool TRIG>
 __device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, uint32_t gs_hi, uint32_t point, PhiloxKey key,
-                                          float c2, float c2m, float2* dump_noise, unsigned long long dump_base) {
+                                          float c2, float c2m, float2* dump_noise, unsigned long long dump_base, const char* s_trig) {
 #pragma unroll 1
   for (int c = 0; c < E / 8; ++c) {
     const uint32_t q2 = 2u * uint32_t((E / 8) * t + c);
@@ -218,13 +244,13 @@ __device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, ui
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t w = j == 0 ? w4.x : j == 1 ? w4.y : j == 2 ? w4.z : w4.w;
-        if (w >= kRefillBelow) continue;
+        if (w >= NoiseWord<TRIG>::kRefillBelow) continue;
         const int i = 8 * c + 4 * h + j;
         const uint4 r = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (1u << 20) | uint32_t(E * t + i), point), key);
         const float u = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r + 0.5) 2^-32
-        const float rad_new = fast_sqrt(c2 * (fast_lg2(u) - 20.0f));
-        const float rad_old = noise20_radius(w, c2, c2m);
-        const float2 d = noise20_dir(w);
+        const float rad_new = fast_sqrt(c2 * (fast_lg2(u) - NoiseWord<TRIG>::kFieldBits));
+        const float rad_old = noise20_radius<TRIG>(w, c2, c2m);
+        const float2 d = noise20_dir<TRIG>(w, s_trig);
         const float2 o = row[i];
         row[i] = make_float2(fmaf(rad_new - rad_old, d.x, o.x), fmaf(rad_new - rad_old, d.y, o.y));
         if (dump_noise) dump_noise[dump_base + i] = make_float2(rad_new * d.x, rad_new * d.y);
@@ -253,16 +279,10 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
   return x;
 }
 
-// OPT bits (measured one by one on the headline shape, profiles/r2_fast_kernel_history.md):
-//   1  noise from 32 bits per complex sample (2 Philox calls per 8 samples + rare refill) instead of 48 (3 calls)
-//   2  FIR with three real products per complex tap (Gauss) instead of four
-constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptDefault = 3;
-
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
           bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2,
-          int TAPS = kFastTaps, int OPT = kOptDefault, int MINB = 1>
-__global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
-  // MINB: blocks per SM the register allocation must allow (2 for the narrow codelets: 64 registers, 32 warps per SM)
+          int TAPS = kFastTaps, int OPT = kOptDefault>
+__global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
   // TAPS: channel taps the FIR evaluates (the host zero-pads the tap table, so a shorter loop only drops exact zeros)
   static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || (!ISI && !FRAMES)), "tap count");
   constexpr bool NOISE32 = (OPT & kOptNoise32) != 0, GAUSS = (OPT & kOptGaussFir) != 0;
@@ -278,7 +298,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   // receiver runs FFT -> equaliser -> IFFT, i.e. the shared transform body serves phases 1 and 2 instead of 0 and 1
   static_assert(!SC || (!ADAPT && !FRAMES), "SC-OFDM: one order on every sample, single link");
   static_assert(!FRAMES || (ADAPT && !DUMP && !REPLAY), "frame batches: fused mode with per-frame tables");
-  using G = FastGeometry<E, T, BLOCK>;
+  using G = FastGeometry<E, T, BLOCK, OPT>;
+  constexpr bool ROLL = (OPT & kOptRollSlicer) != 0 && !DUMP, TRIG = (OPT & kOptTrigTable) != 0, MAX3 = (OPT & kOptMax3) != 0;
   constexpr int N = G::N, RS = G::RS, WORDS = E / 4, W = G::W;
   constexpr int CALLS = (E + 15) / 16;  // Philox calls for E random bytes
   extern __shared__ float4 smem4[];
@@ -297,6 +318,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   float2* s_tail = reinterpret_cast<float2*>(reinterpret_cast<float*>(s_eq + N) + G::RED_F) + team_in_block * G::TAIL_F2;
   float2* s_psk = s_tail - team_in_block * G::TAIL_F2 + G::TEAMS * G::TAIL_F2;
   float2* col = buf + trow * RS + tcol;   // strided set: col[W * RS * m]
+  [[maybe_unused]] char* s_trig = reinterpret_cast<char*>(smem4) + G::BASE_BYTES;        // float2[kTrigEntries]
+  // ROLL: word j of this lane's transmitted labels {column word, row word} at s_stash[j * BLOCK]
+  [[maybe_unused]] uint2* s_stash = reinterpret_cast<uint2*>(reinterpret_cast<char*>(smem4) + G::BASE_BYTES + G::TRIG_BYTES) + threadIdx.x;
   auto tsync = [&]() { team_sync<T>(team_in_block); };
 
   // block-resident copies of the twiddle and equaliser tables
@@ -306,6 +330,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   }
   if constexpr (PSK) {
     for (int i = threadIdx.x; i < G::PSK_F2; i += BLOCK) s_psk[i] = __ldg(&p.psk_tab[i]);
+  }
+  if constexpr (TRIG) {   // direction a: angle 2 pi (a + 0.5) / kTrigEntries - pi
+    for (int i = threadIdx.x; i < kTrigEntries; i += BLOCK) {
+      float sn, cs;
+      sincospif((float(i) + 0.5f) * (2.0f / kTrigEntries) - 1.0f, &sn, &cs);
+      reinterpret_cast<float2*>(s_trig)[i] = make_float2(cs, sn);
+    }
   }
   __syncthreads();
 
@@ -607,6 +638,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             v[m] = make_float2(lq, li);
           }
         }
+        if constexpr (ROLL) {
+#pragma unroll
+          for (int j = 0; j < WORDS; ++j) s_stash[j * BLOCK] = make_uint2(txc[j], txr[j]);
+        }
       } else if (!SC || phase == 1) {
         // ---- channel + noise, in place in shared memory, 8 samples per iteration
         //      (channel/models.py:52-55 restricted to P >= L-1 -> circular; noise/models.py:19-22)
@@ -699,7 +734,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
               wmin = min(min(wmin, min(w8[0], w8[1])), min(min(w8[2], w8[3]), min(min(w8[4], w8[5]), min(w8[6], w8[7]))));
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 g = fast_noise20(w8[i], noise_c2, noise_c2m);
+                const float2 g = fast_noise20<TRIG>(w8[i], noise_c2, noise_c2m, s_trig);
                 if constexpr (DUMP) {
                   if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
                 }
@@ -730,9 +765,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           for (int i = 0; i < 8; ++i) prev[i] = cur[i];
         }
         if constexpr (!REPLAY && NOISE32) {
-          if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line
-            noise_refill<E, NROUNDS>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
-                                     s * (unsigned long long)(N + P) + noise_off + E * t);
+          if (wmin < NoiseWord<TRIG>::kRefillBelow)   // probability 2^-20 (2^-17 with the table) per sample: out of line
+            noise_refill<E, NROUNDS, TRIG>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
+                                           s * (unsigned long long)(N + P) + noise_off + E * t, s_trig);
         }
         if constexpr (!REPLAY) {
           if (p.zero_prefix)   // rare link shape: kept out of line so that the hot instruction stream stays small
@@ -897,45 +932,43 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           }
           sigma2 = ss * mmse_c;
         }
-        unsigned rxc[WORDS], rxr[WORDS];
-#pragma unroll
-        for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
-#pragma unroll
-        for (int m = 0; m < E; ++m) {
-          const float2 yv = u[oidx(m)];
-          const int k = t + T * m;
-          const float4 e = s_eq[k];
-          // SC: yv = swap(z~) of time sample k, already equalised and scaled for the slicer
-          const float a = SC ? yv.y : fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
-          const float b = SC ? -yv.x : fmaf(yv.x, e.y, -yv.y * e.x);  // -Im(Y conj A)
-          const float inv = SC ? 1.0f : fast_rcp(e.z + sigma2);
-          if constexpr (DUMP) {
-            if (!SC && active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
-            // 2 (s_k - 1) / knorm_k with knorm_k^2 = 2 (M_k - 1) / 3, M_k = (top + 1)^2
-            const float zu = ADAPT ? 2.f * e.w * rsqrtf(fmaxf((e.w * e.w + 2.f * e.w) * (2.f / 3.f), 1e-30f)) : p.z_unscale;
-            if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);
-          }
-          if constexpr (PSK) {
-            // nearest point = nearest angle: k = rint(arg(z) M / 2 pi) mod M, label = gray(k)
-            const unsigned kh = (unsigned)__float2int_rn(atan2f(-b, a) * p.psk_scale) & ((1u << p.psk_bits) - 1u);
-            rxc[m >> 2] |= (kh ^ (kh >> 1)) << (8 * (m & 3));
-            continue;
-          }
-          // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
-          const float top = ADAPT ? e.w : p.slice_top;
-          const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
-          const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), top, magic);
-          // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
-          rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
-          rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
-        }
         unsigned be = 0, se = 0;
+        // one label word = 4 subcarriers m = 4 j + i of this lane: spectrum y[i], transmitted words wc / wr
+        auto slice_word = [&](int j, const float2 (&y)[4], unsigned wc, unsigned wr) {
+          unsigned rc = 0u, rr = 0u;
 #pragma unroll
-        for (int j = 0; j < WORDS; ++j) {
+          for (int i = 0; i < 4; ++i) {
+            const float2 yv = y[i];
+            const int k = t + T * (4 * j + i);
+            const float4 e = s_eq[k];
+            // SC: yv = swap(z~) of time sample k, already equalised and scaled for the slicer
+            const float a = SC ? yv.y : fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
+            const float b = SC ? -yv.x : fmaf(yv.x, e.y, -yv.y * e.x);  // -Im(Y conj A)
+            const float inv = SC ? 1.0f : fast_rcp(e.z + sigma2);
+            if constexpr (DUMP) {
+              if (!SC && active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
+              // 2 (s_k - 1) / knorm_k with knorm_k^2 = 2 (M_k - 1) / 3, M_k = (top + 1)^2
+              const float zu = ADAPT ? 2.f * e.w * rsqrtf(fmaxf((e.w * e.w + 2.f * e.w) * (2.f / 3.f), 1e-30f)) : p.z_unscale;
+              if (active && p.dump_z) p.dump_z[s * N + k] = make_float2(a * inv * zu, -b * inv * zu);
+            }
+            if constexpr (PSK) {
+              // nearest point = nearest angle: k = rint(arg(z) M / 2 pi) mod M, label = gray(k)
+              const unsigned kh = (unsigned)__float2int_rn(atan2f(-b, a) * p.psk_scale) & ((1u << p.psk_bits) - 1u);
+              rc |= (kh ^ (kh >> 1)) << (8 * i);
+              continue;
+            }
+            // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
+            const float top = ADAPT ? e.w : p.slice_top;
+            const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
+            const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), top, magic);
+            // accumulate 2*index into byte i of the packed word; the 0x4B000000 parts cancel below
+            rc += __float_as_uint(tc) << (8 * i + 1);
+            rr += __float_as_uint(tr) << (8 * i + 1);
+          }
           // sum over the 4 bytes of (0x4B000000 << (8i+1)) mod 2^32: only i = 0 survives
           constexpr unsigned K = (0x4B000000u << 1);
           if constexpr (PSK) {
-            const unsigned d = rxc[j] ^ txc[j];
+            const unsigned d = rc ^ wc;
             be += __popc(d);
             unsigned any = d | (d >> 4);
             any |= any >> 2;
@@ -946,15 +979,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int k = t + T * (4 * j + i);
-                  if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((txc[j] >> (8 * i)) & 0xffu);
-                  if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((rxc[j] >> (8 * i)) & 0xffu);
+                  if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((wc >> (8 * i)) & 0xffu);
+                  if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((rc >> (8 * i)) & 0xffu);
                 }
               }
             }
-            continue;
+            return;
           }
-          const unsigned dc = ((rxc[j] - K) ^ txc[j]) & 0x1E1E1E1Eu;
-          const unsigned dr = ((rxr[j] - K) ^ txr[j]) & 0x1E1E1E1Eu;
+          const unsigned dc = ((rc - K) ^ wc) & 0x1E1E1E1Eu;
+          const unsigned dr = ((rr - K) ^ wr) & 0x1E1E1E1Eu;
           be += __popc(inv_gray_fields(dc) & 0x1E1E1E1Eu) + __popc(inv_gray_fields(dr) & 0x1E1E1E1Eu);
           // a byte of dc | dr is at most 0x1E: adding 0x7F sets its bit 7 exactly when it is non-zero, without carries
           se += __popc(((dc | dr) + 0x7F7F7F7Fu) & 0x80808080u);
@@ -963,14 +996,41 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int m = 4 * j + i, k = t + T * m;
-                const unsigned ct = (txc[j] >> (8 * i + 1)) & 15u, rt = (txr[j] >> (8 * i + 1)) & 15u;
-                const unsigned cr = ((rxc[j] - K) >> (8 * i + 1)) & 15u, rr = ((rxr[j] - K) >> (8 * i + 1)) & 15u;
+                const unsigned ct = (wc >> (8 * i + 1)) & 15u, rt = (wr >> (8 * i + 1)) & 15u;
+                const unsigned cr = ((rc - K) >> (8 * i + 1)) & 15u, rw = ((rr - K) >> (8 * i + 1)) & 15u;
                 auto ig = [](unsigned x) { x ^= x >> 1; x ^= x >> 2; return x & 15u; };
                 const int hb = ADAPT ? __popc((fmask[ADAPT ? j : 0] >> (8 * i)) & 0xffu) : p.half_bits;
                 if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((ig(rt) << hb) | ig(ct));
-                if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rr) << hb) | ig(cr));
+                if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rw) << hb) | ig(cr));
               }
             }
+          }
+        };
+        if constexpr ((OPT & 32) != 0) {   // DIAGNOSTIC ONLY (tools/microbench): no slicer, the spectrum's power is the only consumer
+          be = __float_as_uint(sigma2) & 1u;
+        } else if constexpr (ROLL) {
+          // the spectrum into this lane's own row (element m at row[m]); nobody else touches the row any more
+          if constexpr (W > 1) tsync();   // ... once the team has finished the column reads of the last pass
+#pragma unroll
+          for (int m = 0; m < E; m += 2) {
+            const float2 a = u[oidx(m)], b = u[oidx(m + 1)];
+            *reinterpret_cast<float4*>(row + m) = make_float4(a.x, a.y, b.x, b.y);
+          }
+#pragma unroll(WORDS >= 4 ? 2 : 1)
+          for (int j = 0; j < WORDS; ++j) {
+            const float4 q0 = *reinterpret_cast<const float4*>(row + 4 * j), q1 = *reinterpret_cast<const float4*>(row + 4 * j + 2);
+            const uint2 w = s_stash[j * BLOCK];
+            const float2 y[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
+            slice_word(j, y, w.x, w.y);
+          }
+          // the next writers of this row: the lane's own row stores of the next transform (program order), or - recorded
+          // bits staged in the buffer, single-carrier column writes - other lanes
+          if constexpr (REPLAY || SC) tsync();
+        } else {
+#pragma unroll
+          for (int j = 0; j < WORDS; ++j) {
+            const float2 y[4] = {u[oidx(4 * j)], u[oidx(4 * j + 1)], u[oidx(4 * j + 2)], u[oidx(4 * j + 3)]};
+            slice_word(j, y, txc[j], txr[j]);
           }
         }
         if (active) {

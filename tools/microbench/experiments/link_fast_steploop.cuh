@@ -98,6 +98,7 @@ struct FastParams {
   unsigned int n_frames, chunks_per_frame, chunk_syms;
   const void* noise;        // complex64 (noise_f64 = 0) or complex128 (noise_f64 = 1); NULL = noiseless
   int noise_f64;
+  unsigned int stagger;     // SYNC >= 3: start delay per warp group, in SM clock cycles
 };
 
 template <int E, int T_ = E, int BLOCK_ = 512>
@@ -107,10 +108,7 @@ struct FastGeometry {
   static constexpr int N = E * T;
   static constexpr int W = T / E;             // radix of the third pass (1: two-pass transform)
   static constexpr int RS = E + 2;            // row stride (complex): conflict-free 128-bit row accesses
-  // float2 per team: T rows of E samples; teams narrower than a half-warp are offset by half a bank cycle (64 B) so that
-  // the 64-bit column accesses of the two teams of a half-warp fall on different banks (ncu: 2-way conflicts on every
-  // column access at N = 64 without the offset, profiles/r2_small_n.md)
-  static constexpr int TEAM_F2 = T * RS + ((T < 16 && (T * RS) % 16 == 0) ? 8 : 0);
+  static constexpr int TEAM_F2 = T * RS;      // float2 per team: T rows of E samples
   static constexpr int BLOCK = BLOCK_;
   static constexpr int TEAMS = BLOCK / T;
   static constexpr int TW2_F2 = E * RS;       // pass-2 twiddles (float2): one padded row per lane column, read as 128-bit pairs
@@ -143,6 +141,18 @@ __device__ __forceinline__ void section_sync() {
     __syncthreads();
   } else if constexpr (SYNC == 2) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + ((threadIdx.x >> 5) & 3)), "n"(BLOCK / 4) : "memory");
+  } else if constexpr (SYNC == 3) {   // groups of 4 consecutive warps (one per scheduler), staggered at kernel start
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (threadIdx.x >> 7)), "n"(128) : "memory");
+  } else if constexpr (SYNC == 4) {   // two groups of BLOCK / 64 consecutive warps (two per scheduler), staggered
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (threadIdx.x / (BLOCK / 2))), "n"(BLOCK / 2) : "memory");
+  }
+}
+template <int SYNC, int BLOCK>
+__device__ __forceinline__ void section_stagger(unsigned cycles) {
+  if constexpr (SYNC == 3 || SYNC == 4) {
+    const unsigned g = SYNC == 3 ? threadIdx.x >> 7 : threadIdx.x / (BLOCK / 2);
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)g * cycles) {}
   }
 }
 
@@ -260,9 +270,8 @@ constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptDefault = 3;
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
           bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2,
-          int TAPS = kFastTaps, int OPT = kOptDefault, int MINB = 1>
-__global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
-  // MINB: blocks per SM the register allocation must allow (2 for the narrow codelets: 64 registers, 32 warps per SM)
+          int TAPS = kFastTaps, int OPT = kOptDefault>
+__global__ void __launch_bounds__(BLOCK) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
   // TAPS: channel taps the FIR evaluates (the host zero-pads the tap table, so a shorter loop only drops exact zeros)
   static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || (!ISI && !FRAMES)), "tap count");
   constexpr bool NOISE32 = (OPT & kOptNoise32) != 0, GAUSS = (OPT & kOptGaussFir) != 0;
@@ -308,6 +317,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
     for (int i = threadIdx.x; i < G::PSK_F2; i += BLOCK) s_psk[i] = __ldg(&p.psk_tab[i]);
   }
   __syncthreads();
+
+  section_stagger<SYNC, BLOCK>(p.stagger);
 
   const PhiloxKey key{(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
   const int P = p.prefix_len;
@@ -506,365 +517,385 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         tsync();
     };
 
-    // OFDM: rolled, ONE copy of the transform body serves both phases (instruction cache).  SC-OFDM: unrolled, so
-    // that the hand-over of the equalised spectrum in registers between phases 1 and 2 has exact live ranges.
-#pragma unroll(SC ? 3 : 1)
-    for (int phase = 0; phase < (halo ? 1 : (SC ? 3 : 2)); ++phase) {
-      section_sync<SYNC, BLOCK>();
-      if (phase == 0) {
-        // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
-        //      low nibble -> column (in-phase) index, high nibble -> row (quadrature) index.
-        if constexpr (REPLAY) {
-          // the symbol's N*bps/8 bytes -> shared memory as big-endian words (coalesced loads); label k = t + T m is
-          // the bps bits at bit offset k*bps, MSB first (constellation/models.py:226-243): a funnel shift over two
-          // words.  column = gray(label & (s-1)), row = gray(label >> log2 s); gray is applied on packed words.
-          const int bps = PSK ? p.psk_bits : 2 * p.half_bits;
-          // ADAPT: the symbol starts at any bit of the stream and every subcarrier has its own width and offset
-          const int intra = ADAPT ? (int)((s * (unsigned long long)p.bits_per_ofdm) & 31) : 0;
-          const int sym_words = ADAPT ? (intra + (int)p.bits_per_ofdm + 31) >> 5 : N * bps / 32;
-          unsigned* wscr = reinterpret_cast<unsigned*>(buf);
+    // ---- bits -> QAM levels (constellation/models.py:180-249). One random byte per subcarrier:
+    //      low nibble -> column (in-phase) index, high nibble -> row (quadrature) index.
+    auto map_symbols = [&]() {
+      if constexpr (REPLAY) {
+        // the symbol's N*bps/8 bytes -> shared memory as big-endian words (coalesced loads); label k = t + T m is
+        // the bps bits at bit offset k*bps, MSB first (constellation/models.py:226-243): a funnel shift over two
+        // words.  column = gray(label & (s-1)), row = gray(label >> log2 s); gray is applied on packed words.
+        const int bps = PSK ? p.psk_bits : 2 * p.half_bits;
+        // ADAPT: the symbol starts at any bit of the stream and every subcarrier has its own width and offset
+        const int intra = ADAPT ? (int)((s * (unsigned long long)p.bits_per_ofdm) & 31) : 0;
+        const int sym_words = ADAPT ? (intra + (int)p.bits_per_ofdm + 31) >> 5 : N * bps / 32;
+        unsigned* wscr = reinterpret_cast<unsigned*>(buf);
 #pragma unroll
-          for (int j = 0; j < PF; ++j)
-            if (t + T * j < sym_words) wscr[t + T * j] = __byte_perm(next_bits[j], 0u, 0x0123);
-          if (t == 0) wscr[sym_words] = 0u;
-          // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
-          replay_prefetch(ISI ? (halo ? chain_lo : s + 1) : s + s_stride);
-          tsync();
+        for (int j = 0; j < PF; ++j)
+          if (t + T * j < sym_words) wscr[t + T * j] = __byte_perm(next_bits[j], 0u, 0x0123);
+        if (t == 0) wscr[sym_words] = 0u;
+        // one OFDM symbol ahead: this team's next recorded bits into registers, its noise towards L2
+        replay_prefetch(ISI ? (halo ? chain_lo : s + 1) : s + s_stride);
+        tsync();
 #pragma unroll
-          for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
-          const unsigned smask = (1u << p.half_bits) - 1u;
-          const int bit0 = t * bps, tb = T * bps;
+        for (int j = 0; j < WORDS; ++j) txc[j] = txr[j] = 0u;
+        const unsigned smask = (1u << p.half_bits) - 1u;
+        const int bit0 = t * bps, tb = T * bps;
 #pragma unroll
-          for (int m = 0; m < E; ++m) {
-            if constexpr (ADAPT) {
-              const int hb = __popc((fmask[ADAPT ? m >> 2 : 0] >> (8 * (m & 3))) & 0xffu);   // log2 of the side
-              const int bit = intra + (int)__ldg(&p.bit_offsets[t + T * m]), w = bit >> 5;
-              const unsigned win = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31);
-              const unsigned lab = hb ? win >> (32 - 2 * hb) : 0u;
-              txc[m >> 2] |= (lab & ((1u << hb) - 1u)) << (8 * (m & 3) + 1);
-              txr[m >> 2] |= (lab >> hb) << (8 * (m & 3) + 1);
-              continue;
-            }
-            const int bit = bit0 + m * tb, w = bit >> 5;
-            const unsigned lab = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31) >> (32 - bps);
-            if constexpr (PSK) {
-              txc[m >> 2] |= lab << (8 * (m & 3));
-            } else {
-              txc[m >> 2] |= (lab & smask) << (8 * (m & 3) + 1);
-              txr[m >> 2] |= (lab >> p.half_bits) << (8 * (m & 3) + 1);
+        for (int m = 0; m < E; ++m) {
+          if constexpr (ADAPT) {
+            const int hb = __popc((fmask[ADAPT ? m >> 2 : 0] >> (8 * (m & 3))) & 0xffu);   // log2 of the side
+            const int bit = intra + (int)__ldg(&p.bit_offsets[t + T * m]), w = bit >> 5;
+            const unsigned win = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31);
+            const unsigned lab = hb ? win >> (32 - 2 * hb) : 0u;
+            txc[m >> 2] |= (lab & ((1u << hb) - 1u)) << (8 * (m & 3) + 1);
+            txr[m >> 2] |= (lab >> hb) << (8 * (m & 3) + 1);
+            continue;
+          }
+          const int bit = bit0 + m * tb, w = bit >> 5;
+          const unsigned lab = __funnelshift_l(wscr[w + 1], wscr[w], bit & 31) >> (32 - bps);
+          if constexpr (PSK) {
+            txc[m >> 2] |= lab << (8 * (m & 3));
+          } else {
+            txc[m >> 2] |= (lab & smask) << (8 * (m & 3) + 1);
+            txr[m >> 2] |= (lab >> p.half_bits) << (8 * (m & 3) + 1);
+          }
+        }
+        if constexpr (!PSK) {
+#pragma unroll
+          for (int j = 0; j < WORDS; ++j) {
+            const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
+            txc[j] = (txc[j] ^ (txc[j] >> 1)) & fm;
+            txr[j] = (txr[j] ^ (txr[j] >> 1)) & fm;
+          }
+        }
+        tsync();
+      } else {
+#pragma unroll
+        for (int c = 0; c < CALLS; ++c) {
+          const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), point), key);
+          const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * c + j < WORDS) {
+              const unsigned fm = ADAPT ? fmask[ADAPT ? 4 * c + j : 0] : p.field_mask;
+              if constexpr (PSK) {
+                txc[4 * c + j] = ww[j] & p.field_mask;   // one label per byte (field_mask = M - 1 in every byte)
+                txr[4 * c + j] = 0u;
+              } else {
+                txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
+                txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
+              }
             }
           }
-          if constexpr (!PSK) {
+        }
+      }
+      // level = 2*index - (s-1) as float via the mantissa of 2^23 + 2*index; re/im swapped so the
+      // forward FFT below computes the inverse transform
+      const float cen = -(magic + p.slice_top);
+      if constexpr (PSK) {
 #pragma unroll
-            for (int j = 0; j < WORDS; ++j) {
-              const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
-              txc[j] = (txc[j] ^ (txc[j] >> 1)) & fm;
-              txr[j] = (txr[j] ^ (txr[j] >> 1)) & fm;
+        for (int m = 0; m < E; ++m) {
+          const float2 pt = s_psk[(txc[m >> 2] >> (8 * (m & 3))) & 0xffu];
+          v[m] = make_float2(pt.y, pt.x);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < (PSK ? 0 : E); ++m) {
+        const unsigned fc = __byte_perm(txc[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
+        const unsigned fr = __byte_perm(txr[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
+        if constexpr (ADAPT) {
+          // per-subcarrier side s_k and power normalisation: (f - (2^23 + s_k - 1)) is the exact integer level
+          const float2 g = __ldg(&level_tab[t + T * m]);
+          v[m] = make_float2(-(__uint_as_float(fr) + g.y) * g.x, (__uint_as_float(fc) + g.y) * g.x);
+        } else {
+          const float li = __uint_as_float(fc) + cen;        // I level:  2*col - (s-1)
+          const float lq = -(__uint_as_float(fr) + cen);     // Q level: (s-1) - 2*row
+          v[m] = make_float2(lq, li);
+        }
+      }
+    };
+
+    auto channel = [&]() {
+      // ---- channel + noise, in place in shared memory, 8 samples per iteration
+      //      (channel/models.py:52-55 restricted to P >= L-1 -> circular; noise/models.py:19-22)
+      float2 prev[8];
+      {
+        const float2* hrow = buf + ((t + T - 1) % T) * RS + (E - 8);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float4 q = *reinterpret_cast<const float4*>(hrow + i);
+          prev[i] = make_float2(q.x, q.y);
+          prev[i + 1] = make_float2(q.z, q.w);
+        }
+      }
+      [[maybe_unused]] float2 new_tail;
+      if constexpr (ISI) {
+        // sample -j before the body (j = 8 - i): inside the cyclic prefix for j <= P (the wrap-around above), else
+        // sample N - (j - P) of the previous OFDM symbol
+        if (t == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (8 - i > P) prev[i] = s_tail[i + P];
+        }
+        if (t < G::TAIL_F2) new_tail = buf[(T - 1) * RS + (E - 8) + t];   // this symbol's tail, before the FIR overwrites it
+      }
+      tsync();
+      if constexpr (ISI) {
+        if (t < G::TAIL_F2) s_tail[t] = new_tail;   // read again only in the next symbol's channel phase
+      }
+      [[maybe_unused]] uint32_t wmin = 0xffffffffu;   // NOISE32: smallest noise word of this lane (refill test)
+      [[maybe_unused]] float ps[8];                   // GAUSS: re + im of the halo samples
+      if constexpr (GAUSS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ps[i] = prev[i].x + prev[i].y;
+      }
+#pragma unroll FIR_UNROLL
+      for (int c = 0; c < E / 8; ++c) {
+        float2 cur[8], y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float4 q = *reinterpret_cast<const float4*>(row + 8 * c + i);
+          cur[i] = make_float2(q.x, q.y);
+          cur[i + 1] = make_float2(q.z, q.w);
+        }
+        if constexpr (GAUSS) {
+          // h x = (k1 - k3) + j (k1 + k2) with k1 = h_re (x_re + x_im), k2 = (h_im - h_re) x_re, k3 = (h_re + h_im) x_im:
+          // three sums over the taps, every product a 2-register FFMA with the tap in the constant bank
+          float cs[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cs[i] = cur[i].x + cur[i].y;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float k1 = 0.f, k2 = 0.f, k3 = 0.f;
+#pragma unroll
+            for (int l = 0; l < TAPS; ++l) {
+              const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
+              const float xs = (i - l >= 0) ? cs[i - l] : ps[8 + i - l];
+              const float4 h = FRAMES ? s_hdr.taps3[l] : p.taps3[l];
+              k1 = fmaf(h.x, xs, k1);
+              k2 = fmaf(h.y, x.x, k2);
+              k3 = fmaf(h.z, x.y, k3);
             }
+            y[i] = make_float2(k1 - k3, k1 + k2);
           }
-          tsync();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ps[i] = cs[i];
         } else {
 #pragma unroll
-          for (int c = 0; c < CALLS; ++c) {
-            const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), point), key);
-            const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+          for (int i = 0; i < 8; ++i) {
+            float yr = 0.f, yi = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (4 * c + j < WORDS) {
-                const unsigned fm = ADAPT ? fmask[ADAPT ? 4 * c + j : 0] : p.field_mask;
-                if constexpr (PSK) {
-                  txc[4 * c + j] = ww[j] & p.field_mask;   // one label per byte (field_mask = M - 1 in every byte)
-                  txr[4 * c + j] = 0u;
-                } else {
-                  txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
-                  txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
-                }
+            for (int l = 0; l < TAPS; ++l) {
+              const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
+              const float2 h = FRAMES ? s_hdr.taps[l] : p.taps[l];
+              yr = fmaf(h.x, x.x, yr);
+              yr = fmaf(-h.y, x.y, yr);
+              yi = fmaf(h.x, x.y, yi);
+              yi = fmaf(h.y, x.x, yi);
+            }
+            y[i] = make_float2(yr, yi);
+          }
+        }
+        {  // unconditional (sigma = 0 scales the samples to zero): keeping FIR and noise in ONE basic block
+           // lets ptxas interleave the Philox / MUFU chains with the FIR's FFMAs
+          if constexpr (!REPLAY && NOISE32) {
+            // 8 complex samples from 2 Philox calls: one word per sample (20-bit radius field, 12-bit angle field)
+            const uint32_t q2 = 2u * uint32_t((E / 8) * t + c);
+            const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q2, point), key);
+            const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q2 + 1u), point), key);
+            const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            wmin = min(min(wmin, min(w8[0], w8[1])), min(min(w8[2], w8[3]), min(min(w8[4], w8[5]), min(w8[6], w8[7]))));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 g = fast_noise20(w8[i], noise_c2, noise_c2m);
+              if constexpr (DUMP) {
+                if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
               }
+              y[i] = cadd(y[i], g);
+            }
+          } else if constexpr (!REPLAY) {
+            // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
+            const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
+            const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, point), key);
+            const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), point), key);
+            const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), point), key);
+            const uint32_t rw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const uint32_t aw[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 g = fast_noise(rw[i], aw[i >> 1], (i & 1) ? 0x7632u : 0x7610u, noise_c2);
+              if constexpr (DUMP) {
+                if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
+              }
+              y[i] = cadd(y[i], g);
             }
           }
         }
-        // level = 2*index - (s-1) as float via the mantissa of 2^23 + 2*index; re/im swapped so the
-        // forward FFT below computes the inverse transform
-        const float cen = -(magic + p.slice_top);
-        if constexpr (PSK) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2)
+          *reinterpret_cast<float4*>(row + 8 * c + i) = make_float4(y[i].x, y[i].y, y[i + 1].x, y[i + 1].y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) prev[i] = cur[i];
+      }
+      if constexpr (!REPLAY && NOISE32) {
+        if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line
+          noise_refill<E, NROUNDS>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
+                                   s * (unsigned long long)(N + P) + noise_off + E * t);
+      }
+      if constexpr (!REPLAY) {
+        if (p.zero_prefix)   // rare link shape: kept out of line so that the hot instruction stream stays small
+          zero_prefix_tail_noise<E, NROUNDS>(row, t, P, gs_lo, gs_hi, point, key, noise_c2,
+                                             (DUMP && active) ? p.dump_noise : nullptr, s * (unsigned long long)(N + P) + N);
+      }
+      tsync();
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m] = col[W * RS * m];
+      if constexpr (REPLAY) {
+        // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples (the lines
+        // were pulled into L2 one OFDM symbol ago)
+        const unsigned long long ni = (active ? s : 0ull) * (unsigned long long)(N + P) + noise_off + t;
+        if (p.noise && !p.noise_f64) {
+          const float2* nz = reinterpret_cast<const float2*>(p.noise) + ni;
+#pragma unroll
+          for (int m = 0; m < E; ++m) v[m] = cadd(v[m], __ldg(nz + T * m));
+        } else if (p.noise) {
+          const double2* nz = reinterpret_cast<const double2*>(p.noise) + ni;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
-            const float2 pt = s_psk[(txc[m >> 2] >> (8 * (m & 3))) & 0xffu];
-            v[m] = make_float2(pt.y, pt.x);
+            const double2 g = __ldg(nz + T * m);
+            v[m] = cadd(v[m], make_float2((float)g.x, (float)g.y));
           }
         }
+        if (p.zero_prefix && p.noise) {
+          // overlap-add of the recorded tail noise: stream sample N + n onto sample n = t + T m < P
 #pragma unroll
-        for (int m = 0; m < (PSK ? 0 : E); ++m) {
-          const unsigned fc = __byte_perm(txc[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
-          const unsigned fr = __byte_perm(txr[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
-          if constexpr (ADAPT) {
-            // per-subcarrier side s_k and power normalisation: (f - (2^23 + s_k - 1)) is the exact integer level
-            const float2 g = __ldg(&level_tab[t + T * m]);
-            v[m] = make_float2(-(__uint_as_float(fr) + g.y) * g.x, (__uint_as_float(fc) + g.y) * g.x);
-          } else {
-            const float li = __uint_as_float(fc) + cen;        // I level:  2*col - (s-1)
-            const float lq = -(__uint_as_float(fr) + cen);     // Q level: (s-1) - 2*row
-            v[m] = make_float2(lq, li);
-          }
-        }
-      } else if (!SC || phase == 1) {
-        // ---- channel + noise, in place in shared memory, 8 samples per iteration
-        //      (channel/models.py:52-55 restricted to P >= L-1 -> circular; noise/models.py:19-22)
-        float2 prev[8];
-        {
-          const float2* hrow = buf + ((t + T - 1) % T) * RS + (E - 8);
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float4 q = *reinterpret_cast<const float4*>(hrow + i);
-            prev[i] = make_float2(q.x, q.y);
-            prev[i + 1] = make_float2(q.z, q.w);
-          }
-        }
-        [[maybe_unused]] float2 new_tail;
-        if constexpr (ISI) {
-          // sample -j before the body (j = 8 - i): inside the cyclic prefix for j <= P (the wrap-around above), else
-          // sample N - (j - P) of the previous OFDM symbol
-          if (t == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (8 - i > P) prev[i] = s_tail[i + P];
-          }
-          if (t < G::TAIL_F2) new_tail = buf[(T - 1) * RS + (E - 8) + t];   // this symbol's tail, before the FIR overwrites it
-        }
-        tsync();
-        if constexpr (ISI) {
-          if (t < G::TAIL_F2) s_tail[t] = new_tail;   // read again only in the next symbol's channel phase
-        }
-        [[maybe_unused]] uint32_t wmin = 0xffffffffu;   // NOISE32: smallest noise word of this lane (refill test)
-        [[maybe_unused]] float ps[8];                   // GAUSS: re + im of the halo samples
-        if constexpr (GAUSS) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ps[i] = prev[i].x + prev[i].y;
-        }
-#pragma unroll FIR_UNROLL
-        for (int c = 0; c < E / 8; ++c) {
-          float2 cur[8], y[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float4 q = *reinterpret_cast<const float4*>(row + 8 * c + i);
-            cur[i] = make_float2(q.x, q.y);
-            cur[i + 1] = make_float2(q.z, q.w);
-          }
-          if constexpr (GAUSS) {
-            // h x = (k1 - k3) + j (k1 + k2) with k1 = h_re (x_re + x_im), k2 = (h_im - h_re) x_re, k3 = (h_re + h_im) x_im:
-            // three sums over the taps, every product a 2-register FFMA with the tap in the constant bank
-            float cs[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cs[i] = cur[i].x + cur[i].y;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float k1 = 0.f, k2 = 0.f, k3 = 0.f;
-#pragma unroll
-              for (int l = 0; l < TAPS; ++l) {
-                const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
-                const float xs = (i - l >= 0) ? cs[i - l] : ps[8 + i - l];
-                const float4 h = FRAMES ? s_hdr.taps3[l] : p.taps3[l];
-                k1 = fmaf(h.x, xs, k1);
-                k2 = fmaf(h.y, x.x, k2);
-                k3 = fmaf(h.z, x.y, k3);
+          for (int m = 0; m < E; ++m) {
+            if (t + T * m < P) {
+              const unsigned long long ti = ni + N + T * m;
+              float2 g;
+              if (p.noise_f64) {
+                const double2 d = __ldg(reinterpret_cast<const double2*>(p.noise) + ti);
+                g = make_float2((float)d.x, (float)d.y);
+              } else {
+                g = __ldg(reinterpret_cast<const float2*>(p.noise) + ti);
               }
-              y[i] = make_float2(k1 - k3, k1 + k2);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ps[i] = cs[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float yr = 0.f, yi = 0.f;
-#pragma unroll
-              for (int l = 0; l < TAPS; ++l) {
-                const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
-                const float2 h = FRAMES ? s_hdr.taps[l] : p.taps[l];
-                yr = fmaf(h.x, x.x, yr);
-                yr = fmaf(-h.y, x.y, yr);
-                yi = fmaf(h.x, x.y, yi);
-                yi = fmaf(h.y, x.x, yi);
-              }
-              y[i] = make_float2(yr, yi);
+              v[m] = cadd(v[m], g);
             }
           }
-          {  // unconditional (sigma = 0 scales the samples to zero): keeping FIR and noise in ONE basic block
-             // lets ptxas interleave the Philox / MUFU chains with the FIR's FFMAs
-            if constexpr (!REPLAY && NOISE32) {
-              // 8 complex samples from 2 Philox calls: one word per sample (20-bit radius field, 12-bit angle field)
-              const uint32_t q2 = 2u * uint32_t((E / 8) * t + c);
-              const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q2, point), key);
-              const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q2 + 1u), point), key);
-              const uint32_t w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-              wmin = min(min(wmin, min(w8[0], w8[1])), min(min(w8[2], w8[3]), min(min(w8[4], w8[5]), min(w8[6], w8[7]))));
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 g = fast_noise20(w8[i], noise_c2, noise_c2m);
-                if constexpr (DUMP) {
-                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
-                }
-                y[i] = cadd(y[i], g);
-              }
-            } else if constexpr (!REPLAY) {
-              // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
-              const uint32_t q3 = 3u * uint32_t((E / 8) * t + c);
-              const uint4 wa = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | q3, point), key);
-              const uint4 wb = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 1u), point), key);
-              const uint4 wc = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (q3 + 2u), point), key);
-              const uint32_t rw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-              const uint32_t aw[4] = {wc.x, wc.y, wc.z, wc.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float2 g = fast_noise(rw[i], aw[i >> 1], (i & 1) ? 0x7632u : 0x7610u, noise_c2);
-                if constexpr (DUMP) {
-                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
-                }
-                y[i] = cadd(y[i], g);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; i += 2)
-            *reinterpret_cast<float4*>(row + 8 * c + i) = make_float4(y[i].x, y[i].y, y[i + 1].x, y[i + 1].y);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) prev[i] = cur[i];
-        }
-        if constexpr (!REPLAY && NOISE32) {
-          if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line
-            noise_refill<E, NROUNDS>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
-                                     s * (unsigned long long)(N + P) + noise_off + E * t);
-        }
-        if constexpr (!REPLAY) {
-          if (p.zero_prefix)   // rare link shape: kept out of line so that the hot instruction stream stays small
-            zero_prefix_tail_noise<E, NROUNDS>(row, t, P, gs_lo, gs_hi, point, key, noise_c2,
-                                               (DUMP && active) ? p.dump_noise : nullptr, s * (unsigned long long)(N + P) + N);
-        }
-        tsync();
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = col[W * RS * m];
-        if constexpr (REPLAY) {
-          // recorded noise, added in the transposed layout: consecutive lanes read consecutive samples (the lines
-          // were pulled into L2 one OFDM symbol ago)
-          const unsigned long long ni = (active ? s : 0ull) * (unsigned long long)(N + P) + noise_off + t;
-          if (p.noise && !p.noise_f64) {
-            const float2* nz = reinterpret_cast<const float2*>(p.noise) + ni;
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = cadd(v[m], __ldg(nz + T * m));
-          } else if (p.noise) {
-            const double2* nz = reinterpret_cast<const double2*>(p.noise) + ni;
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-              const double2 g = __ldg(nz + T * m);
-              v[m] = cadd(v[m], make_float2((float)g.x, (float)g.y));
-            }
-          }
-          if (p.zero_prefix && p.noise) {
-            // overlap-add of the recorded tail noise: stream sample N + n onto sample n = t + T m < P
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-              if (t + T * m < P) {
-                const unsigned long long ti = ni + N + T * m;
-                float2 g;
-                if (p.noise_f64) {
-                  const double2 d = __ldg(reinterpret_cast<const double2*>(p.noise) + ti);
-                  g = make_float2((float)d.x, (float)d.y);
-                } else {
-                  g = __ldg(reinterpret_cast<const float2*>(p.noise) + ti);
-                }
-                v[m] = cadd(v[m], g);
-              }
-            }
-          }
-        }
-        tsync();
-        section_sync<SYNC, BLOCK>();
-      }
-
-      // ---- forward FFT of N = E*T points: radix-E in registers, row/column exchange, twiddle, radix-E; when the
-      //      team is wider than E a second exchange and a radix-W pass follow (Stockham: natural order throughout)
-      float2 u[E];
-      // element t + T m of the transform: u[oidx(m)]
-      auto oidx = [](int m) constexpr { return W > 1 ? m : fft_out_index<E>(m); };
-      if constexpr (SC) {
-        if (phase == 0) {
-          // no transform at the single-carrier transmitter: the levels are the time samples
-          tx_epilogue([&](int m) { return make_float2(v[m].y, v[m].x); });
-          continue;
         }
       }
-      {
-      fft_dit_inplace<E, -1>(v);
-#pragma unroll
-      for (int r = 0; r < E; r += 2) {
-        const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
-        *reinterpret_cast<float4*>(row + r) = make_float4(a.x, a.y, b.x, b.y);
-      }
-      tsync();
-#pragma unroll
-      for (int m = 0; m < E; ++m) u[m] = col[W * RS * m];
       tsync();
       section_sync<SYNC, BLOCK>();
+    };
+
+    // ---- One rolled loop over the radix-E passes of the symbol's transforms, so that the kernel holds ONE copy of the
+    //      codelet and of every exchange (the loop body must stay inside the 32 KB instruction cache: beyond it the
+    //      warps of an SM, which run free, are fetch-bound - tools/microbench/icache.cu).  A forward FFT of N = E*T
+    //      points is an even step (radix-E in registers, rows to shared memory) and an odd step (columns back, twiddle,
+    //      radix-E; a second exchange and a radix-W pass when the team is wider than E; Stockham: natural order
+    //      throughout).  OFDM: steps 0-1 transmitter (IFFT as FFT of swapped data), 2-3 receiver.  SC-OFDM: the
+    //      transmitter has no transform, steps 2-3 are the receiver's FFT and 4-5 its IFFT.
+    // element t + T m of a finished transform: v[oidx(m)]
+    auto oidx = [](int m) constexpr { return W > 1 ? m : fft_out_index<E>(m); };
+    if constexpr (SC) {
+      section_sync<SYNC, BLOCK>();
+      map_symbols();
+      // no transform at the single-carrier transmitter: the levels are the time samples
+      tx_epilogue([&](int m) { return make_float2(v[m].y, v[m].x); });
+    }
+    const int step_end = halo ? 2 : (SC ? 6 : 4);
+#pragma unroll 1
+    for (int step = SC ? 2 : 0; step < step_end; ++step) {
+      if (step & 1) {
 #pragma unroll
-      for (int c = 0; c < E - 1; c += 2) {   // twiddles of legs c + 1 and c + 2 in one 128-bit load (row stride RS: conflict-free)
-        const float4 w = *reinterpret_cast<const float4*>(s_tw + tcol * RS + c);
-        u[c + 1] = cmul(u[c + 1], make_float2(w.x, w.y));
-        if (c + 2 < E) u[c + 2] = cmul(u[c + 2], make_float2(w.z, w.w));
+        for (int m = 0; m < E; ++m) v[m] = col[W * RS * m];
+        tsync();
+        section_sync<SYNC, BLOCK>();
+#pragma unroll
+        for (int c = 0; c < E - 1; c += 2) {   // twiddles of legs c + 1 and c + 2 in one 128-bit load (row stride RS: conflict-free)
+          const float4 w = *reinterpret_cast<const float4*>(s_tw + tcol * RS + c);
+          v[c + 1] = cmul(v[c + 1], make_float2(w.x, w.y));
+          if (c + 2 < E) v[c + 2] = cmul(v[c + 2], make_float2(w.z, w.w));
+        }
+      } else {
+        section_sync<SYNC, BLOCK>();
+        if (!SC && step == 0) {
+          map_symbols();
+        } else if (step == 2) {
+          channel();
+        }   // step 4 (SC-OFDM): v already holds swap(Z~)
       }
-      fft_dit_inplace<E, -1>(u);
+      fft_dit_inplace<E, -1>(v);
+      if (!(step & 1)) {
+#pragma unroll
+        for (int r = 0; r < E; r += 2) {
+          const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
+          *reinterpret_cast<float4*>(row + r) = make_float4(a.x, a.y, b.x, b.y);
+        }
+        tsync();
+        continue;
+      }
       if constexpr (W > 1) {
         // pass-2 output r of butterfly j = t lands at linear index E*E*(t/E) + E*r + (t%E); reload the strided
-        // set; radix-W butterflies j = t + T q over the legs u[q + r Q], twiddles W_N^(j r), results in place
+        // set; radix-W butterflies j = t + T q over the legs v[q + r Q], twiddles W_N^(j r), results in place
         constexpr int Q = E / W;
         float2* blk = buf + (E * trow) * RS + tcol;
 #pragma unroll
-        for (int r = 0; r < E; ++r) blk[r * RS] = u[fft_out_index<E>(r)];
+        for (int r = 0; r < E; ++r) blk[r * RS] = v[fft_out_index<E>(r)];
         tsync();
 #pragma unroll
-        for (int m = 0; m < E; ++m) u[m] = col[W * RS * m];
+        for (int m = 0; m < E; ++m) v[m] = col[W * RS * m];
         const float2* s_tw3 = s_tw + G::TW2_F2;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const float2 w1 = s_tw3[t + T * q];
           if constexpr (W == 2) {
-            const float2 a = u[q], b = cmul(u[q + Q], w1);
-            u[q] = cadd(a, b);
-            u[q + Q] = csub(a, b);
+            const float2 a = v[q], b = cmul(v[q + Q], w1);
+            v[q] = cadd(a, b);
+            v[q + Q] = csub(a, b);
           } else {
             const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-            const float2 a0 = u[q], a1 = cmul(u[q + Q], w1), a2 = cmul(u[q + 2 * Q], w2), a3 = cmul(u[q + 3 * Q], w3);
+            const float2 a0 = v[q], a1 = cmul(v[q + Q], w1), a2 = cmul(v[q + 2 * Q], w2), a3 = cmul(v[q + 3 * Q], w3);
             const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
             const float2 jd = make_float2(d13.y, -d13.x);   // -j (a1 - a3)
-            u[q] = cadd(s02, s13);
-            u[q + Q] = cadd(d02, jd);
-            u[q + 2 * Q] = csub(s02, s13);
-            u[q + 3 * Q] = csub(d02, jd);
+            v[q] = cadd(s02, s13);
+            v[q + Q] = cadd(d02, jd);
+            v[q + 2 * Q] = csub(s02, s13);
+            v[q + 3 * Q] = csub(d02, jd);
           }
         }
       }
-      }
 
-      if (phase == 0) {
-        // ---- x~[t + T m] = swap(u[brev m])
-        tx_epilogue([&](int m) { const float2 o = u[oidx(m)]; return make_float2(o.y, o.x); });
-      } else if (SC && phase == 1) {
-        // ---- SC-OFDM: equalise in the frequency domain and hand swap(Z) to the inverse transform of phase 2
+      if (!SC && step == 1) {
+        // ---- x~[t + T m] = swap(v[brev m])
+        tx_epilogue([&](int m) { const float2 o = v[oidx(m)]; return make_float2(o.y, o.x); });
+        continue;
+      }
+      // per-symbol MMSE noise estimate from the spectrum's power; branch-free (mmse_c = 0 for ZF / none) so that the
+      // shuffle latency overlaps the per-subcarrier products below
+      float sigma2 = 0.f;
+      if (!SC || step == 3) {
         float sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
+        for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(v[m].x, v[m].x, fmaf(v[m].y, v[m].y, sq[m & 3]));
         float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
 #pragma unroll
         for (int off = (T < 32 ? T : 32) / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-        if constexpr (T > 32) {
+        if constexpr (T > 32) {   // the team spans T / 32 warps
           if (lane == 0) s_red[t / 32] = ss;
           tsync();
           ss = 0.f;
 #pragma unroll
           for (int i = 0; i < T / 32; ++i) ss += s_red[i];
         }
-        const float sigma2 = ss * mmse_c;
+        sigma2 = ss * mmse_c;
+      }
+      if (SC && step == 3) {
+        // ---- SC-OFDM: equalise in the frequency domain and hand swap(Z~) to the inverse transform of steps 4-5
+        float2 z[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-          const float2 yv = u[oidx(m)];
+          const float2 yv = v[oidx(m)];
           const int k = t + T * m;
           const float4 e = s_eq[k];
           const float a = fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
@@ -873,38 +904,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           if constexpr (DUMP) {
             if (active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
           }
-          v[m] = make_float2(-b * inv, a * inv);          // swap(Z~): the forward transform then computes the inverse
+          z[m] = make_float2(-b * inv, a * inv);          // swap(Z~): the forward transform then computes the inverse
         }
-      } else {
-        // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
-        //      simulation/models.py:597-606)
-        // per-symbol MMSE noise estimate; branch-free (mmse_c = 0 for ZF / none) so that the shuffle latency
-        // overlaps the per-subcarrier products below
-        float sigma2 = 0.f;
-        if constexpr (!SC) {
-          float sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
-          float ss = (sq[0] + sq[1]) + (sq[2] + sq[3]);
+        for (int m = 0; m < E; ++m) v[m] = z[m];
+        continue;
+      }
+      // ---- equaliser + slicer + error count (equalization/models.py:22-63, constellation/models.py:19-27,
+      //      simulation/models.py:597-606).  Counters-only kernels of the wide codelets run it as a rolled loop over
+      //      PARTS parts of the lane's subcarriers (static code size): after a part, the registers of the next part -
+      //      spectrum and transmitted label words - move into the registers of the first.
+      constexpr int PARTS = (!DUMP && E >= 32) ? 2 : 1;
+      constexpr int EP = E / PARTS, WP = WORDS / PARTS;
+      unsigned be = 0, se = 0;
+#pragma unroll 1
+      for (int h = 0; h < PARTS; ++h) {
+        unsigned rxc[WP], rxr[WP];
 #pragma unroll
-          for (int off = (T < 32 ? T : 32) / 2; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-          if constexpr (T > 32) {   // the team spans T / 32 warps
-            if (lane == 0) s_red[t / 32] = ss;
-            tsync();
-            ss = 0.f;
+        for (int j = 0; j < WP; ++j) rxc[j] = rxr[j] = 0u;
+        const float4* eq_part = s_eq + t + T * EP * h;
 #pragma unroll
-            for (int i = 0; i < T / 32; ++i) ss += s_red[i];
-          }
-          sigma2 = ss * mmse_c;
-        }
-        unsigned rxc[WORDS], rxr[WORDS];
-#pragma unroll
-        for (int j = 0; j < WORDS; ++j) rxc[j] = rxr[j] = 0u;
-#pragma unroll
-        for (int m = 0; m < E; ++m) {
-          const float2 yv = u[oidx(m)];
-          const int k = t + T * m;
-          const float4 e = s_eq[k];
+        for (int mm = 0; mm < EP; ++mm) {
+          const float2 yv = v[oidx(mm)];
+          const float4 e = eq_part[T * mm];
+          [[maybe_unused]] const int k = t + T * (mm + EP * h);
           // SC: yv = swap(z~) of time sample k, already equalised and scaled for the slicer
           const float a = SC ? yv.y : fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
           const float b = SC ? -yv.x : fmaf(yv.x, e.y, -yv.y * e.x);  // -Im(Y conj A)
@@ -918,20 +941,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           if constexpr (PSK) {
             // nearest point = nearest angle: k = rint(arg(z) M / 2 pi) mod M, label = gray(k)
             const unsigned kh = (unsigned)__float2int_rn(atan2f(-b, a) * p.psk_scale) & ((1u << p.psk_bits) - 1u);
-            rxc[m >> 2] |= (kh ^ (kh >> 1)) << (8 * (m & 3));
+            rxc[mm >> 2] |= (kh ^ (kh >> 1)) << (8 * (mm & 3));
             continue;
           }
           // sat() clamps to the outermost levels, the 2^23 trick rounds to the nearest level index
           const float top = ADAPT ? e.w : p.slice_top;
           const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
           const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), top, magic);
-          // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
-          rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
-          rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
+          // accumulate 2*index into byte (mm & 3) of the packed word; the 0x4B000000 parts cancel below
+          rxc[mm >> 2] += __float_as_uint(tc) << (8 * (mm & 3) + 1);
+          rxr[mm >> 2] += __float_as_uint(tr) << (8 * (mm & 3) + 1);
         }
-        unsigned be = 0, se = 0;
 #pragma unroll
-        for (int j = 0; j < WORDS; ++j) {
+        for (int j = 0; j < WP; ++j) {
           // sum over the 4 bytes of (0x4B000000 << (8i+1)) mod 2^32: only i = 0 survives
           constexpr unsigned K = (0x4B000000u << 1);
           if constexpr (PSK) {
@@ -973,11 +995,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             }
           }
         }
-        if (active) {
-          acc_bit_err += be;
-          acc_sym_err += se;
-          acc_syms += E;
+        if constexpr (PARTS > 1) {
+          if (h + 1 < PARTS) {
+#pragma unroll
+            for (int i = 0; i < (PARTS - 1) * EP; ++i) v[oidx(i)] = v[oidx(i + EP)];
+#pragma unroll
+            for (int j = 0; j < (PARTS - 1) * WP; ++j) {
+              txc[j] = txc[j + WP];
+              txr[j] = txr[j + WP];
+            }
+          }
         }
+      }
+      if (active) {
+        acc_bit_err += be;
+        acc_sym_err += se;
+        acc_syms += E;
       }
     }
     if constexpr (ISI) {
