@@ -148,6 +148,30 @@ int ofdm_link_launch_sweep(ofdm_link* link, int32_t n_points, const double* snr_
                            uint64_t seed, uint32_t first_point, uint64_t first_symbol, uint64_t n_symbols, void* stream);
 int ofdm_link_read_sweep(ofdm_link* link, void* stream, int32_t n_points, ofdm_link_result* out);
 int ofdm_link_pack_sweep(ofdm_link* link, double* payload_dev, int32_t rank, int32_t world, void* stream);
+/* Post-equaliser stage of the reference's water-filling robustness experiment
+ * (examples/waterfilling_noise_bump_experiment.py:163-183; the per-subcarrier variant of examples/overview.py:210-214
+ * is the rx_gain of ofdm_link_create_loaded).  After the equaliser and before the demapper the link then
+ *   1. adds coloured noise of variance 10^(-snr_db/10) * noise_profile[k] on subcarrier k (:163-171) - from Philox stream 3
+ *      in fused mode, or the recorded matrix `recorded_noise` ([n_symbols][N] complex128, as the reference drew it) in
+ *      replay mode (HOST memory for ofdm_link_run_replay, DEVICE memory for ofdm_link_launch_replay);
+ *   2. applies rx_gain (:173-176);
+ *   3. accumulates sum |z|^2 and the number of values when `measure_power` is set (:178-179, read them with
+ *      ofdm_link_read_z_power);
+ *   4. multiplies by z_scale (:180-181): the caller's second pass over the same seed / recorded streams with
+ *      z_scale = 1 / sqrt(sum / count) of the first pass.
+ * The reference normalises over the whole run, so the two passes are two launches over the same symbol range.
+ * A link with a post stage runs on the general kernel.  post = NULL removes the stage. */
+typedef struct ofdm_link_post {
+  const double* noise_profile; /* [N] >= 0, or NULL = no injected noise                                      */
+  const void* recorded_noise;  /* replay mode only, or NULL                                                   */
+  double z_scale;              /* 1.0 = none                                                                  */
+  int32_t measure_power;       /* 1: accumulate sum |z|^2 (before z_scale)                                    */
+  int32_t reserved;
+} ofdm_link_post;
+int ofdm_link_set_post(ofdm_link* link, const ofdm_link_post* post);
+/* sum |z|^2 and the number of equalised values since the last ofdm_link_reset_counters (the synchronous run_* calls
+ * reset first); synchronises `stream` */
+int ofdm_link_read_z_power(ofdm_link* link, void* stream, double* sum_abs2, uint64_t* n_values);
 /* kernel launches issued by this library since load (for bench.py's gpu_launches) */
 uint64_t ofdm_b200_launch_count(void);
 

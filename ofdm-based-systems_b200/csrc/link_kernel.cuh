@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(Geometry<N, E>::BLOCK) ofdm_link_kernel(const 
 
   unsigned long long acc_bit_err = 0, acc_sym_err = 0, acc_bits = 0, acc_syms = 0;
   double acc_pow = 0.0;
+  double acc_zpow = 0.0;
   float acc_max = 0.f;
 
   float2 v[E];
@@ -412,9 +413,37 @@ __global__ void __launch_bounds__(Geometry<N, E>::BLOCK) ofdm_link_kernel(const 
         r[m] = cmul(r[m], make_float2(e.x, e.y));
       }
     }
-    if (p.rx_gain) {  // receiver compensation of the applied power loading (examples/waterfilling_noise_bump_experiment.py:165-169)
+    if (p.post_sigma) {  // coloured noise injected AFTER the equaliser (examples/waterfilling_noise_bump_experiment.py:163-171)
+      if (p.post_src == SRC_REPLAY_F64) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const double2 g = __ldg(reinterpret_cast<const double2*>(p.post_noise) + s * (unsigned long long)N + t + T * m);
+          r[m] = cadd(r[m], make_float2((float)g.x, (float)g.y));
+        }
+      } else {
+        uint4 w = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          if ((m & 1) == 0)
+            w = philox4x32<10>(make_uint4((uint32_t)gs, (uint32_t)(gs >> 32), (3u << 28) | uint32_t((m >> 1) * T + t), p.point), key);
+          const float2 g = (m & 1) ? box_muller(w.z, w.w) : box_muller(w.x, w.y);
+          r[m] = cadd(r[m], cscale(g, p.post_scale * __ldg(&p.post_sigma[t + T * m])));
+        }
+      }
+    }
+    if (p.rx_gain) {  // receiver compensation of the applied power loading (examples/waterfilling_noise_bump_experiment.py:173-176)
 #pragma unroll
       for (int m = 0; m < E; ++m) r[m] = cscale(r[m], __ldg(&p.sc_tab[t + T * m]).w);
+    }
+    if (p.z_power) {     // block-wide mean power of what the demapper would see (:178-179): first pass of the renormalisation
+      float zp = 0.f;
+#pragma unroll
+      for (int m = 0; m < E; ++m) zp = fmaf(r[m].x, r[m].x, fmaf(r[m].y, r[m].y, zp));
+      acc_zpow += (double)zp;
+    }
+    if (p.z_scale != 1.0f) {   // ... and its second pass (:180-181)
+#pragma unroll
+      for (int m = 0; m < E; ++m) r[m] = cscale(r[m], p.z_scale);
     }
     if (p.modulator == MOD_SC) {  // SC-OFDM: back to the time domain (modulation/models.py:89)
       team_fft<N, E, +1>(r, buf, p.tw, team);
@@ -464,11 +493,12 @@ __global__ void __launch_bounds__(Geometry<N, E>::BLOCK) ofdm_link_kernel(const 
   __syncwarp();
   const unsigned long long b0 = warp_sum64(acc_bit_err), b1 = warp_sum64(acc_bits), b2 = warp_sum64(acc_sym_err),
                            b3 = warp_sum64(acc_syms);
-  double pw = acc_pow;
+  double pw = acc_pow, zw = acc_zpow;
   float mx = acc_max;
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     pw += __shfl_down_sync(0xffffffffu, pw, off);
+    zw += __shfl_down_sync(0xffffffffu, zw, off);
     mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, off));
   }
   if ((threadIdx.x & 31) == 0) {
@@ -477,6 +507,10 @@ __global__ void __launch_bounds__(Geometry<N, E>::BLOCK) ofdm_link_kernel(const 
     if (b2) atomicAdd(&p.counters[CNT_SYM_ERRORS], b2);
     if (b3) atomicAdd(&p.counters[CNT_SYMBOLS], b3);
     if (pw != 0.0) atomicAdd(p.tx_power_sum, pw);
+    if (p.z_power) {
+      atomicAdd(reinterpret_cast<double*>(&p.counters[CNT_Z_POWER]), zw);
+      if (b3) atomicAdd(&p.counters[CNT_Z_VALUES], b3);
+    }
     atomicMax(p.tx_power_max_bits, (unsigned long long)__double_as_longlong((double)mx));
   }
   if (t == 0 && s1 > s0) atomicAdd(&p.counters[CNT_OFDM_SYMBOLS], s1 - s0);

@@ -11,7 +11,8 @@ enum : int { MOD_OFDM = 0, MOD_SC = 1 };
 enum : int { EQ_NONE = 0, EQ_ZF = 1, EQ_MMSE = 2 };
 enum : int { SCHEME_QAM = 0, SCHEME_PSK = 1 };
 enum : int { SRC_NONE = 0, SRC_PHILOX = 1, SRC_REPLAY_F32 = 2, SRC_REPLAY_F64 = 3 };
-enum : int { CNT_BIT_ERRORS = 0, CNT_BITS = 1, CNT_SYM_ERRORS = 2, CNT_SYMBOLS = 3, CNT_OFDM_SYMBOLS = 4, CNT_WORDS = 8 };
+enum : int { CNT_BIT_ERRORS = 0, CNT_BITS = 1, CNT_SYM_ERRORS = 2, CNT_SYMBOLS = 3, CNT_OFDM_SYMBOLS = 4,
+              CNT_Z_VALUES = 5 /* equalised values whose power was summed */, CNT_Z_POWER = 6 /* sum |z|^2, a double */, CNT_WORDS = 8 };
 
 struct LinkParams {
   // ---- link shape
@@ -36,6 +37,13 @@ struct LinkParams {
   unsigned long long bits_len;
   const void* noise;  // complex64 or complex128 over the serial stream, (N+P) per symbol
   unsigned long long compare_limit;
+  // ---- post-equaliser stage (examples/waterfilling_noise_bump_experiment.py:163-183)
+  const float* post_sigma;  // [N] per-component standard deviation of the coloured noise for unit noise power, or NULL
+  float post_scale;         // sqrt(noise power) = 10^(-snr_db/20)
+  int post_src;             // SRC_PHILOX (stream tag 3) | SRC_REPLAY_F64 (recorded matrix [sym][N] complex128)
+  const void* post_noise;
+  float z_scale;            // multiplies every equalised value before the demapper (1/sqrt(avg_power), :178-181)
+  int z_power;              // 1: accumulate sum |z|^2 (before z_scale) and the count into the counter block
   // ---- outputs
   unsigned long long* counters;  // [CNT_WORDS]
   double* tx_power_sum;          // sum |tx|^2 over every tx sample (prefix included)

@@ -196,6 +196,12 @@ void fill_params(const ofdm_link* L, LinkParams& p, double snr_db) {
   p.counters = L->d_cnt->cnt;
   p.tx_power_sum = &L->d_cnt->power_sum;
   p.tx_power_max_bits = &L->d_cnt->power_max_bits;
+  // post-equaliser stage (ofdm_link_set_post); the replay entry points switch post_src to the recorded matrix
+  p.post_sigma = L->d_post;
+  p.post_scale = (float)std::pow(10.0, -snr_db / 20.0);
+  p.post_src = SRC_PHILOX;
+  p.z_scale = (float)L->z_scale;
+  p.z_power = L->z_power;
 }
 
 void set_dump(LinkParams& p, const ofdm_link_dump* d) {
@@ -619,6 +625,7 @@ void ofdm_link_destroy(ofdm_link* L) {
   // the cached arena may be handed to the next link at once: everything this link queued on the device must be done
   cudaDeviceSynchronize();
   if (L->d_sweep) cudaFree(L->d_sweep);
+  if (L->d_post) cudaFree(L->d_post);
   g_arenas.release(L->arena, L->table_bytes, L->device);
   delete L;
 }
@@ -646,6 +653,56 @@ int ofdm_link_debug_tables(const ofdm_link* L, float* eq, float* level, uint32_t
   fill_fast(L, f, 0.0, nullptr);
   if (taps) std::memcpy(taps, f.taps, sizeof(f.taps));
   if (taps3) std::memcpy(taps3, f.taps3, sizeof(f.taps3));
+  return OFDM_OK;
+}
+
+int ofdm_link_set_post(ofdm_link* L, const ofdm_link_post* post) {
+  if (!L) return fail(OFDM_EINVAL, "null link");
+  DeviceGuard guard(L->device);
+  const int N = L->d.n_subcarriers;
+  const bool active = post && (post->noise_profile || post->z_scale != 1.0 || post->measure_power);
+  if (!active) {   // back to the plain chain (and to the fast kernel, if the shape has one)
+    if (L->d_post) cudaFree(L->d_post);
+    L->d_post = nullptr;
+    L->post_recorded = nullptr;
+    L->z_scale = 1.0;
+    L->z_power = 0;
+    if (L->fast_shape) L->fast = L->fast_shape;
+    L->fast_shape = 0;
+    return OFDM_OK;
+  }
+  if (!(post->z_scale > 0.0) || !std::isfinite(post->z_scale)) return fail(OFDM_EINVAL, "z_scale must be positive and finite");
+  if (post->noise_profile) {
+    std::vector<float> sig(N);
+    for (int k = 0; k < N; ++k) {
+      const double v = post->noise_profile[k];
+      if (!(v >= 0.0) || !std::isfinite(v)) return fail(OFDM_EINVAL, "noise_profile[%d] must be finite and non-negative", k);
+      sig[k] = (float)std::sqrt(v / 2.0);
+    }
+    if (!L->d_post) CUDA_TRY(cudaMalloc(&L->d_post, N * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(L->d_post, sig.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+  } else if (L->d_post) {
+    cudaFree(L->d_post);
+    L->d_post = nullptr;
+  }
+  L->post_recorded = post->noise_profile ? post->recorded_noise : nullptr;
+  L->z_scale = post->z_scale;
+  L->z_power = post->measure_power ? 1 : 0;
+  if (L->fast) {   // the stage lives in the general kernel
+    L->fast_shape = L->fast;
+    L->fast = 0;
+  }
+  return OFDM_OK;
+}
+
+int ofdm_link_read_z_power(ofdm_link* L, void* stream, double* sum_abs2, uint64_t* n_values) {
+  if (!L || !sum_abs2 || !n_values) return fail(OFDM_EINVAL, "null argument");
+  DeviceGuard guard(L->device);
+  CounterBlock h;
+  CUDA_TRY(cudaMemcpyAsync(&h, L->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  std::memcpy(sum_abs2, &h.cnt[CNT_Z_POWER], sizeof(double));
+  *n_values = h.cnt[CNT_Z_VALUES];
   return OFDM_OK;
 }
 
@@ -735,6 +792,11 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
   p.sym_count = n_symbols;
   p.limit_bits = compare_limit_bits != 0;
   p.compare_limit = compare_limit_bits;
+  if (L->d_post) {   // recorded post-equaliser noise, or none (a replayed run never draws from Philox)
+    p.post_src = SRC_REPLAY_F64;
+    p.post_noise = L->post_recorded;
+    if (!L->post_recorded) p.post_sigma = nullptr;
+  }
   set_dump(p, dump_dev);
   return launch(L, p, (cudaStream_t)stream);
 }
@@ -858,11 +920,23 @@ int ofdm_link_run_replay(ofdm_link* L, double snr_db, const uint8_t* bits, uint6
   cudaError_t e = cudaMemcpy(d_bits, bits, n_bytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && noise_bytes) e = cudaMemcpy(d_noise, noise, noise_bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cleanup(); return fail(OFDM_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e)); }
+  // recorded post-equaliser noise: HOST memory here, staged on the device for the launch
+  const void* post_host = L->post_recorded;
+  void* d_post_noise = nullptr;
+  if (L->d_post && post_host) {
+    const size_t bytes = n_symbols * size_t(L->d.n_subcarriers) * 16;
+    e = cudaMalloc(&d_post_noise, bytes ? bytes : 16);
+    if (e == cudaSuccess) e = cudaMemcpy(d_post_noise, post_host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cleanup(); cudaFree(d_post_noise); return fail(OFDM_ECUDA, "staging the recorded post-equaliser noise failed: %s", cudaGetErrorString(e)); }
+    L->post_recorded = d_post_noise;
+  }
   rc = ofdm_link_reset_counters(L, nullptr);
   if (!rc) rc = ofdm_link_launch_replay(L, snr_db, d_bits, n_bytes, d_noise, noise_dtype, n_symbols, compare_limit_bits,
                                         dump ? &stage.dev : nullptr, nullptr);
   if (!rc) rc = read_counters(L, nullptr, out);
   if (!rc) rc = stage.fetch();
+  L->post_recorded = post_host;
+  cudaFree(d_post_noise);
   cleanup();
   return rc;
 }

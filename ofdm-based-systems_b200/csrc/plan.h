@@ -70,6 +70,12 @@ struct ofdm_link {
   float2* d_tw_fast = nullptr;  // pass-2 twiddles [(r-1)*E + k], then the pass-3 base twiddles exp(-2 pi i j / N)
   float2 taps_fast[8];
   double knorm = 1.0;
+  // post-equaliser stage (ofdm_link_set_post): links with one run on the general kernel
+  int fast_shape = 0;           // what `fast` was before a post stage switched the link to the general kernel
+  float* d_post = nullptr;      // [N] sqrt(noise_profile / 2), own allocation
+  const void* post_recorded = nullptr;   // recorded noise matrix for the replay entry points (caller's memory)
+  double z_scale = 1.0;
+  int z_power = 0;
 };
 
 namespace ofdm {

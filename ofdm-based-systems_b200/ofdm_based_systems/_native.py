@@ -57,12 +57,18 @@ class LinkDump(C.Structure):
                 ("noise", C.c_void_p)]
 
 
+class LinkPost(C.Structure):
+    _fields_ = [("noise_profile", C.c_void_p), ("recorded_noise", C.c_void_p), ("z_scale", C.c_double),
+                ("measure_power", C.c_int32), ("reserved", C.c_int32)]
+
+
 EXPORTS = (
     "ofdm_b200_last_error", "ofdm_b200_abi_version", "ofdm_b200_device_count", "ofdm_b200_launch_count",
     "ofdm_b200_measure_fp32_tflops", "ofdm_link_create", "ofdm_link_create_loaded", "ofdm_link_destroy", "ofdm_link_bits_per_ofdm_symbol", "ofdm_link_table_bytes",
     "ofdm_link_uses_fast_kernel",
     "ofdm_link_run_fused", "ofdm_link_run_replay", "ofdm_link_launch_fused", "ofdm_link_launch_replay",
     "ofdm_link_run_sweep", "ofdm_link_launch_sweep", "ofdm_link_read_sweep", "ofdm_link_pack_sweep",
+    "ofdm_link_set_post", "ofdm_link_read_z_power",
     "ofdm_link_reset_counters", "ofdm_link_read_result", "ofdm_link_counters_device_ptr", "ofdm_link_pack_counters",
     "ofdm_waterfill_bitload_batched", "ofdm_waterfill_bitload_batched_dev", "ofdm_frames_run",
     "ofdm_link_debug_tables", "ofdm_frames_debug_tables", "ofdm_frames_header_floats",
@@ -98,6 +104,8 @@ def _load() -> C.CDLL:
     lib.ofdm_link_launch_sweep.argtypes = [vp, i32, vp, vp, u64, u32, u64, u64, vp]
     lib.ofdm_link_read_sweep.argtypes = [vp, vp, i32, vp]
     lib.ofdm_link_pack_sweep.argtypes = [vp, vp, i32, i32, vp]
+    lib.ofdm_link_set_post.argtypes = [vp, C.POINTER(LinkPost)]
+    lib.ofdm_link_read_z_power.argtypes = [vp, vp, C.POINTER(dbl), C.POINTER(u64)]
     lib.ofdm_link_reset_counters.argtypes = [vp, vp]
     lib.ofdm_link_read_result.argtypes = [vp, vp, C.POINTER(LinkResult)]
     lib.ofdm_link_counters_device_ptr.argtypes = [vp]
@@ -254,6 +262,43 @@ class Link:
         out = LinkCounters.from_struct(res)
         return (out, arrs) if dump else out
 
+    # ---- post-equaliser stage (ofdm_link_set_post): coloured noise after the equaliser, block-wide renormalisation
+    def set_post(self, noise_profile: Optional[np.ndarray] = None, *, recorded_noise: Optional[np.ndarray] = None,
+                 z_scale: float = 1.0, measure_power: bool = False) -> None:
+        """examples/waterfilling_noise_bump_experiment.py:163-183.  ``noise_profile`` [N]: variance multipliers of the noise
+        injected after the equaliser (variance 10^(-snr_db/10) * profile[k]); ``recorded_noise`` [n_symbols, N] complex128:
+        the matrix the reference drew (replay mode); ``z_scale``: factor applied before the demapper; ``measure_power``:
+        accumulate sum |z|^2 for ``read_z_power``.  All defaults = remove the stage."""
+        prof = None if noise_profile is None else np.ascontiguousarray(noise_profile, dtype=np.float64)
+        if prof is not None and prof.shape != (self.n_subcarriers,):
+            raise ValueError("noise_profile must have one entry per subcarrier")
+        rec = None if recorded_noise is None else np.ascontiguousarray(recorded_noise, dtype=np.complex128)
+        self._post_keepalive = (prof, rec)        # the library reads the recorded matrix at run time
+        post = LinkPost(None if prof is None else prof.ctypes.data, None if rec is None else rec.ctypes.data,
+                        float(z_scale), int(bool(measure_power)), 0)
+        _check(lib.ofdm_link_set_post(self._h, C.byref(post)))
+        self.uses_fast_kernel = bool(lib.ofdm_link_uses_fast_kernel(self._h))
+
+    def read_z_power(self, stream: int = 0):
+        """(sum |z|^2, number of equalised values) accumulated since the counters were last reset."""
+        total, count = C.c_double(), C.c_uint64()
+        _check(lib.ofdm_link_read_z_power(self._h, stream, C.byref(total), C.byref(count)))
+        return float(total.value), int(count.value)
+
+    def run_fused_renormalised(self, snr_db: float, noise_sigma: float, n_symbols: int, *, noise_profile=None,
+                               seed: int = 0x0FD3, point: int = 0, first_symbol: int = 0, dump: Optional[tuple] = None):
+        """The two passes of the reference's block-wide renormalisation (:178-181) over the same Philox streams: the first
+        measures the mean power of the equalised, compensated values, the second slices them scaled by 1/sqrt(mean)."""
+        self.set_post(noise_profile, measure_power=True)
+        self.run_fused(snr_db, noise_sigma, n_symbols, seed=seed, point=point, first_symbol=first_symbol)
+        total, count = self.read_z_power()
+        avg = total / max(count, 1)
+        self.set_post(noise_profile, z_scale=1.0 / np.sqrt(avg) if avg > 1e-12 else 1.0)
+        try:
+            return self.run_fused(snr_db, noise_sigma, n_symbols, seed=seed, point=point, first_symbol=first_symbol, dump=dump)
+        finally:
+            self.set_post()
+
     # ---- a whole SNR sweep in one launch (ofdm_link_run_sweep / _launch_sweep / _read_sweep / _pack_sweep)
     @staticmethod
     def _sweep_arrays(snr_dbs, noise_sigmas):
@@ -327,6 +372,12 @@ class Link:
         return int(lib.ofdm_link_counters_device_ptr(self._h) or 0)
 
 
+def _reject_null_channels(taps: np.ndarray) -> None:
+    """channel/models.py:41-43: a realisation whose taps are all zero has no unit-energy normalisation."""
+    if taps.size and not np.all(np.any(taps != 0, axis=-1)):
+        raise ValueError("Impulse response cannot be all zeros.")
+
+
 def bit_loading_gap(ser: float, scheme: str = "QAM") -> float:
     """The SNR gap of the reference's bit-loading rules: QAM Qinv(ser/4)^2/3 (constellation/models.py:301-304),
     PSK gamma* = Qinv(ser/2)^2 / (2 pi^2) (:462-464).  scipy's norm.isf, like the reference."""
@@ -348,6 +399,7 @@ def waterfill_bitload_batched(taps: np.ndarray, n_subcarriers: int, snr_db: floa
     taps = np.ascontiguousarray(np.atleast_2d(taps), dtype=np.complex128)
     f, l = taps.shape
     n = int(n_subcarriers)
+    _reject_null_channels(taps)
     desc = WaterfillDesc(n, l, SCHEME[scheme], int(bool(waterfilling)), int(min_order), int(max_order), float(snr_db),
                          float(n if total_power is None else total_power), bit_loading_gap(ser, scheme), float(tolerance),
                          {"gap": 0, "capacity": 1}[order_rule], 0, float(capacity_scaling))
@@ -359,6 +411,10 @@ def waterfill_bitload_batched(taps: np.ndarray, n_subcarriers: int, snr_db: floa
     cap = np.empty((f, n), dtype=np.float64)
     _check(lib.ofdm_waterfill_bitload_batched(C.byref(desc), taps.ctypes.data, f, power.ctypes.data, orders.ctypes.data,
                                               level.ctypes.data, h_eq.ctypes.data, iters.ctypes.data, cap.ctypes.data))
+    if waterfilling and not np.all(np.isfinite(level)):
+        # a spectral null: the reference refuses it (power_allocation/models.py:117-121)
+        bad = int(np.flatnonzero(~np.isfinite(level))[0])
+        raise ValueError(f"All channel gains must be positive, got min={float(np.min(np.abs(h_eq[bad]) ** 2))}")
     return dict(power=power, orders=orders.astype(np.int64), water_level=level, h_eq=h_eq, iterations=iters,
                 capacity=cap)
 
@@ -389,6 +445,7 @@ def run_frames(n_subcarriers: int, n_frames: int, symbols_per_frame: int, snr_db
         if taps.shape[0] != n_frames:
             raise ValueError("taps must hold one row of raw taps per frame")
         n_taps = taps.shape[1]
+        _reject_null_channels(taps)
     n = int(n_subcarriers)
     desc = FramesDesc(n, int(n_taps - 1 if prefix_len is None else prefix_len), EQUALIZER[equalizer], int(n_taps),
                       0 if order is not None else 1, int(order or 0), int(bool(waterfilling)), int(min_order), int(max_order),

@@ -305,6 +305,7 @@ def main():
     link_case("adaptive_psk_n64_zf", 64, 0, "PSK", ch["two_ray"], "CYCLIC", 1, "ZF", 18.0, 24, 34, orders=orders)
 
     loaded_cases(ch)
+    noise_bump_cases(ch)
     ber_study(ch)
 
     # Simulation.run() itself
@@ -384,8 +385,78 @@ def loaded_cases(ch):
                   kind="loaded")
 
 
+def noise_bump_cases(ch):
+    """SURVEY 8f-2, second half: the post-equaliser stage of examples/waterfilling_noise_bump_experiment.py:120-185 run with
+    the reference's OWN components, statement for statement (noise-free channel, power loading, MMSE equaliser, coloured
+    noise injected after the equaliser, receiver compensation, division by the square root of the block's mean power,
+    fixed-order decoder), recording the bits and the noise matrix it drew.  Two of the script's three scenarios at two of
+    its SNR points, shortened to 96 OFDM symbols."""
+    h = ch["Lin-Phoong_P2"]
+    n_sc, order, n_ofdm = 64, 64, 96
+    prefix_len = len(h) - 1
+    H = np.fft.fft(h, n_sc)
+    gains = np.abs(H) ** 2
+    for nm, allocation, bump_db, snr_db, seed in (("uniform_bump3_snr20", "UNIFORM", 3.0, 20.0, 61),
+                                                   ("wf_bump3_snr15", "WATERFILLING", 3.0, 15.0, 62),
+                                                   ("wf_bump6_snr25", "WATERFILLING", 6.0, 25.0, 63)):
+        np.random.seed(seed)
+        gen = Generator(PCG64(seed))
+        profile = np.ones(n_sc)
+        profile[int(0.75 * n_sc):] = 10 ** (bump_db / 10)                      # create_noise_profile, :42-51
+        mapper = QAMConstellationMapper(order=order)
+        s2p = SerialToParallelConverter()
+        prefix = PREFIX["CYCLIC"](prefix_length=prefix_len)
+        channel = ChannelModel(impulse_response=h, snr_db=0.0, noise_model=NoNoiseModel())
+        total_bits = n_ofdm * n_sc * mapper.bits_per_symbol
+        with contextlib.redirect_stdout(io.StringIO()):
+            bits = RandomBitsGenerator(generator=gen).generate_bits(total_bits)
+            tx_bytes = bits.getvalue()
+            bits_list = read_bits_from_stream(bits)
+            symbols = mapper.encode(bits)
+            parallel = s2p.to_parallel(symbols, n_sc)
+            noise_power = 10 ** (-snr_db / 10)
+            if allocation == "WATERFILLING":
+                power = WaterfillingPowerAllocation(total_power=1.0, channel_gains=gains / profile, noise_power=noise_power).allocate()
+                power = np.maximum(power, 1e-4)
+                power = power / np.sum(power)
+            else:
+                power = UniformPowerAllocation(total_power=1.0, num_subcarriers=n_sc).allocate()
+            parallel = parallel * np.sqrt(power)
+            equalizer = EQ["MMSE"](channel_frequency_response=H, snr_db=snr_db)
+            mod = OFDMModulator(num_subcarriers=n_sc, prefix_scheme=prefix, equalizator=equalizer)
+            tx = mod.modulate(parallel)
+            rx = channel.transmit(s2p.to_serial(tx))
+            demod = mod.demodulate(s2p.to_parallel(rx, n_sc + prefix_len))
+            noise_std = np.sqrt(noise_power * profile / 2.0)[np.newaxis, :]
+            noise_matrix = (np.random.normal(size=demod.shape) + 1j * np.random.normal(size=demod.shape)) * noise_std
+            noisy = demod + noise_matrix
+            power_sqrt_safe = np.sqrt(power)
+            power_sqrt_safe[power_sqrt_safe < 1e-10] = 1.0
+            noisy = noisy / power_sqrt_safe
+            z = s2p.to_serial(noisy)
+            avg_power = np.mean(np.abs(z) ** 2)
+            if avg_power > 1e-12:
+                z = z / np.sqrt(avg_power)
+            rx_stream = mapper.decode(z)
+            rx_bytes = rx_stream.getvalue()
+            rx_list = read_bits_from_stream(rx_stream)
+        bit_errors = sum(a != b for a, b in zip(bits_list, rx_list))
+        pw = np.abs(tx) ** 2
+        path = os.path.join(OUT, f"noisebump_{nm}.npz")
+        np.savez_compressed(path, name=nm, n_sc=n_sc, order=order, n_ofdm=n_ofdm, prefix_len=prefix_len, snr_db=snr_db, seed=seed,
+                            taps_raw=h, taps_chan=channel.impulse_response, H_eq=H, eq="MMSE", allocation=allocation,
+                            noise_profile=profile, amp=np.sqrt(power), rx_gain=1.0 / power_sqrt_safe, total_bits=total_bits,
+                            tx_bytes=np.frombuffer(tx_bytes, dtype=np.uint8), post_noise=noise_matrix,
+                            rx_bytes=np.frombuffer(rx_bytes, dtype=np.uint8), received_symbols=z, avg_power=float(avg_power),
+                            bit_errors=int(bit_errors), papr_db=float(10 * np.log10(np.max(pw) / np.mean(pw))))
+        print(f"noisebump_{nm:24s} bits={total_bits} bit_errors={bit_errors} avg_power={avg_power:.5f} {os.path.getsize(path) / 1024:.0f} KB")
+
+
 if __name__ == "__main__":
-    if "--ber-only" in sys.argv:
+    if "--noisebump-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        noise_bump_cases({"Lin-Phoong_P2": np.load(os.path.join(CHAN, "Lin-Phoong_P2.npy"))})
+    elif "--ber-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         names = ["Lin-Phoong_P2", "severe_multipath"]
         ber_study({n: np.load(os.path.join(CHAN, n + ".npy")) for n in names})

@@ -466,11 +466,15 @@ def adaptive_setup(n_sc: int, taps_raw: np.ndarray, snr_db: float, ser: float, s
 
 
 def run_link(setup: LinkSetup, tx_bytes: bytes, total_bits: int, noise: Optional[np.ndarray] = None,
-             normals: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Dict[str, object]:
+             normals: Optional[Tuple[np.ndarray, np.ndarray]] = None, post_noise: Optional[np.ndarray] = None,
+             renormalise: bool = False) -> Dict[str, object]:
     """The hot path ``Simulation.run()`` executes between simulation/models.py:454 and :606, with the
     bits supplied by the caller and the noise either supplied already scaled (``noise``: complex
     array over the serial stream = replay) or as the two standard-normal arrays the reference would
-    draw (``normals``), or absent (no-noise model)."""
+    draw (``normals``), or absent (no-noise model).
+    ``post_noise`` ([S, N] complex, already scaled) and ``renormalise`` restate the post-equaliser stage of
+    examples/waterfilling_noise_bump_experiment.py:163-183: coloured noise added to the equalised subcarriers, then the
+    receiver gains, then the whole block divided by the square root of its mean power."""
     n, p = setup.n_sc, setup.prefix_len
     if setup.adaptive:
         symbols, tx_labels = encode_adaptive(tx_bytes, setup.orders, setup.scheme)
@@ -491,11 +495,16 @@ def run_link(setup: LinkSetup, tx_bytes: bytes, total_bits: int, noise: Optional
     rx_par = rx.reshape(-1, n + p)                                                    # :546-548
     out, Y, Zf = demodulate(rx_par, n, p, setup.prefix_type, setup.eq, setup.H_eq, setup.snr_db,
                             setup.modulator, return_freq=True)                        # :554
+    if post_noise is not None:
+        out = out + np.asarray(post_noise).reshape(out.shape)                         # noise_bump_experiment.py:163-171
     if setup.rx_gain is not None:
         if setup.modulator != MOD_OFDM:
             raise ValueError("receiver power compensation is per subcarrier: OFDM modulator only")
-        out = out * np.asarray(setup.rx_gain, dtype=np.float64)[None, :]              # noise_bump_experiment.py:165-169
+        out = out * np.asarray(setup.rx_gain, dtype=np.float64)[None, :]              # noise_bump_experiment.py:173-176
     z = out.reshape(-1)
+    z_avg_power = float(np.mean(np.abs(z) ** 2)) if z.size else 0.0                   # :178
+    if renormalise and z_avg_power > 1e-12:
+        z = z / np.sqrt(z_avg_power)                                                  # :179-181
     if setup.adaptive:
         rx_bytes, rx_labels = decode_adaptive(z, setup.orders, setup.scheme)          # :591
     else:
@@ -514,7 +523,7 @@ def run_link(setup: LinkSetup, tx_bytes: bytes, total_bits: int, noise: Optional
                 symbol_errors=symbol_errors, total_bits=total_bits,
                 bit_error_rate=(bit_errors / total_bits if total_bits > 0 else 0.0),
                 symbol_error_rate=(symbol_errors / symbols.size if symbols.size else 0.0),
-                papr_db=papr, noise_power=(None if noise is None else float(np.mean(np.abs(conv) ** 2) / 10 ** (setup.snr_db / 10))))
+                papr_db=papr, z_avg_power=z_avg_power, noise_power=(None if noise is None else float(np.mean(np.abs(conv) ** 2) / 10 ** (setup.snr_db / 10))))
 
 
 # --------------------------------------------------------------------------------------------

@@ -24,6 +24,10 @@ def golden_link_names():
     return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "link_*.npz")))
 
 
+def golden_noisebump_names():
+    return sorted(os.path.basename(p)[10:-4] for p in glob.glob(os.path.join(GOLDEN, "noisebump_*.npz")))
+
+
 def golden_loaded_names():
     return sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "loaded_*.npz")))
 

@@ -10,7 +10,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("script", ["quick_start.py", "custom_channel.py", "fresh_channel_per_frame.py"])
+@pytest.mark.parametrize("script", ["quick_start.py", "custom_channel.py", "fresh_channel_per_frame.py", "noise_bump_experiment.py"])
 def test_example_runs(script, tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script)], cwd=tmp_path, capture_output=True, text=True,
                        timeout=300)

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import ofdm_oracle as oc
-from conftest import golden_link_names, golden_loaded_names, load_golden
+from conftest import golden_link_names, golden_loaded_names, golden_noisebump_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -168,3 +168,73 @@ def test_applied_power_loading_replay_matches_reference(name, kernel, monkeypatc
     if not mismatch.any():
         assert res.bit_errors == int(g["bit_errors"]) and res.symbol_errors == int(g["symbol_errors"])
     assert abs(res.papr_db - float(g["papr_db"])) < 2e-4
+
+
+@pytest.mark.parametrize("name", golden_noisebump_names())
+def test_post_equaliser_stage_replay_matches_reference(name):
+    """The post-equaliser stage of examples/waterfilling_noise_bump_experiment.py:163-183 (ofdm_link_set_post) replayed from
+    the reference's recorded bits and noise matrix: first pass = mean power of the compensated values, second pass = the
+    renormalised values through the demapper."""
+    from ofdm_based_systems._native import Link
+    g = load_golden("noisebump", name)
+    n, n_ofdm, order = int(g["n_sc"]), int(g["n_ofdm"]), int(g["order"])
+    link = Link(n, g["taps_chan"], g["H_eq"], np.full(n, order), prefix_type="CYCLIC", prefix_len=int(g["prefix_len"]),
+                equalizer="MMSE", amp=g["amp"], rx_gain=g["rx_gain"])
+    assert link.uses_fast_kernel
+    link.set_post(g["noise_profile"], recorded_noise=g["post_noise"], measure_power=True)
+    assert not link.uses_fast_kernel                      # the stage lives in the general kernel
+    link.run_replay(float(g["snr_db"]), g["tx_bytes"].tobytes(), None, n_ofdm)
+    total, count = link.read_z_power()
+    assert count == n_ofdm * n
+    avg = total / count
+    assert abs(avg - float(g["avg_power"])) < 1e-5 * float(g["avg_power"])
+    link.set_post(g["noise_profile"], recorded_noise=g["post_noise"], z_scale=1.0 / np.sqrt(avg))
+    res, d = link.run_replay(float(g["snr_db"]), g["tx_bytes"].tobytes(), None, n_ofdm, dump=("z", "rx_labels"))
+    link.set_post()
+    assert link.uses_fast_kernel
+    link.close()
+    z_ref = g["received_symbols"].reshape(n_ofdm, n)
+    assert rel_err(d["z"].astype(np.complex128), z_ref) < REL_TOL
+    rx_ref = oc.labels_from_bits(g["rx_bytes"].tobytes(), oc.bits_per_symbol(order)).reshape(n_ofdm, n)
+    mismatch = d["rx_labels"] != rx_ref
+    assert not np.any(mismatch & (oc.qam_boundary_distance(z_ref, order) > BOUNDARY_TAU))
+    if not mismatch.any():
+        assert res.bit_errors == int(g["bit_errors"])
+    assert abs(res.papr_db - float(g["papr_db"])) < 2e-4
+
+
+def test_post_equaliser_stage_fused_statistics():
+    """Fused mode of the same stage (Philox stream 3, two passes over the same seed): the mean power of the compensated
+    values is what the noise profile and the loading predict, the renormalised block has unit power, and the BER agrees
+    with the oracle run on its own random numbers."""
+    from ofdm_based_systems._native import Link
+    g = load_golden("noisebump", "wf_bump6_snr25")
+    n, order, snr = int(g["n_sc"]), int(g["order"]), float(g["snr_db"])
+    link = Link(n, g["taps_chan"], g["H_eq"], np.full(n, order), prefix_type="CYCLIC", prefix_len=int(g["prefix_len"]),
+                equalizer="MMSE", amp=g["amp"], rx_gain=g["rx_gain"])
+    n_ofdm = 20_000
+    link.set_post(g["noise_profile"], measure_power=True)
+    link.run_fused(snr, 0.0, n_ofdm, seed=5)
+    total, count = link.read_z_power()
+    avg = total / count
+    link.set_post(g["noise_profile"], z_scale=1.0 / np.sqrt(avg), measure_power=True)
+    res = link.run_fused(snr, 0.0, n_ofdm, seed=5)
+    total2, _ = link.read_z_power()
+    assert abs(total2 / count - avg) < 1e-6 * avg       # the power is measured before the scale, same streams
+    res2 = link.run_fused_renormalised(snr, 0.0, n_ofdm, noise_profile=g["noise_profile"], seed=5)
+    assert (res2.bit_errors, res2.bits) == (res.bit_errors, res.bits)
+    link.close()
+    # the oracle on NumPy random numbers: 400 OFDM symbols, the OFDM symbol as the unit of the standard error
+    rng = np.random.default_rng(11)
+    setup = oc.LinkSetup(n_sc=n, taps_raw=g["taps_raw"], snr_db=snr, order=order, eq="MMSE", awgn=False,
+                         prefix_len_override=int(g["prefix_len"]), amp=g["amp"], rx_gain=g["rx_gain"])
+    s_ref = 400
+    bits = oc.generate_bits(s_ref * n * 6, rng)
+    std = np.sqrt(10 ** (-snr / 10) * g["noise_profile"] / 2)[None, :]
+    post = (rng.normal(size=(s_ref, n)) + 1j * rng.normal(size=(s_ref, n))) * std
+    ref = oc.run_link(setup, bits, s_ref * n * 6, post_noise=post, renormalise=True)
+    assert abs(avg - ref["z_avg_power"]) < 0.05 * ref["z_avg_power"]
+    tb, rb = oc.unpack_bits(bits), oc.unpack_bits(ref["rx_bytes"])
+    per_symbol = np.mean((tb != rb).reshape(s_ref, n * 6), axis=1)
+    sem = per_symbol.std(ddof=1) / np.sqrt(s_ref)
+    assert abs(res.bit_errors / res.bits - per_symbol.mean()) < 4 * sem + 1e-4

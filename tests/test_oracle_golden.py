@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import ofdm_oracle as oc
-from conftest import golden_loaded_names, golden_link_names, load_golden
+from conftest import golden_loaded_names, golden_link_names, golden_noisebump_names, load_golden
 
 
 def _setup(g):
@@ -177,3 +177,18 @@ def test_applied_power_loading_matches_reference_components(name):
     assert r["rx_bytes"] == g["rx_bytes"].tobytes()
     np.testing.assert_allclose(r["received_symbols"], g["received_symbols"], rtol=0, atol=1e-12)
     assert abs(r["papr_db"] - float(g["papr_db"])) < 1e-10
+
+
+@pytest.mark.parametrize("name", golden_noisebump_names())
+def test_post_equaliser_stage_matches_reference_experiment(name):
+    """coloured noise injected after the equaliser, receiver compensation and the block-wide renormalisation of
+    examples/waterfilling_noise_bump_experiment.py:163-183, recorded from the reference's own components
+    (oracle/make_golden.py::noise_bump_cases)."""
+    g = load_golden("noisebump", name)
+    setup = oc.LinkSetup(n_sc=int(g["n_sc"]), taps_raw=g["taps_raw"], snr_db=float(g["snr_db"]), order=int(g["order"]),
+                         eq="MMSE", awgn=False, prefix_len_override=int(g["prefix_len"]), amp=g["amp"], rx_gain=g["rx_gain"])
+    r = oc.run_link(setup, g["tx_bytes"].tobytes(), int(g["total_bits"]), post_noise=g["post_noise"], renormalise=True)
+    assert r["bit_errors"] == int(g["bit_errors"])
+    assert r["rx_bytes"] == g["rx_bytes"].tobytes()
+    np.testing.assert_allclose(r["received_symbols"], g["received_symbols"], rtol=0, atol=1e-11)
+    assert abs(r["z_avg_power"] - float(g["avg_power"])) < 1e-10 * float(g["avg_power"])

@@ -82,3 +82,14 @@ def test_capacity_rule_and_allocation_comparison_match_oracle():
     assert np.all(cmp_["capacity_gain"] > -1e-9)
     with pytest.raises(ValueError):
         waterfill_bitload_batched(taps, n, snr, order_rule="capacity")          # needs min / max order
+
+
+def test_null_channels_are_refused_like_the_reference():
+    """channel/models.py:41-43 and power_allocation/models.py:117-128: all-zero taps and spectral nulls raise ValueError."""
+    from ofdm_based_systems import _native
+    with pytest.raises(ValueError, match="Impulse response cannot be all zeros"):
+        _native.waterfill_bitload_batched(np.zeros((2, 4), complex), 64, 10.0)
+    with pytest.raises(ValueError, match="Impulse response cannot be all zeros"):
+        _native.run_frames(64, 2, 10, 10.0, taps=np.array([[1.0, 0.5], [0.0, 0.0]], complex), order=16)
+    with pytest.raises(ValueError, match="All channel gains must be positive"):
+        _native.waterfill_bitload_batched(np.array([[1.0, -1.0]], complex), 64, 10.0)     # H[0] = 0
