@@ -256,7 +256,9 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 // OPT bits (measured one by one on the headline shape, profiles/r2_fast_kernel_history.md):
 //   1  noise from 32 bits per complex sample (2 Philox calls per 8 samples + rare refill) instead of 48 (3 calls)
 //   2  FIR with three real products per complex tap (Gauss) instead of four
-constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptDefault = 3;
+//   4  no per-symbol noise estimate: ZF / no equaliser, where sigma2 = 0 (the MMSE form then needs neither the power sum
+//      over the spectrum nor its shuffles; -3 instructions per subcarrier)
+constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptNoEstimate = 4, kOptDefault = 3;
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
           bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2,
@@ -881,7 +883,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         // per-symbol MMSE noise estimate; branch-free (mmse_c = 0 for ZF / none) so that the shuffle latency
         // overlaps the per-subcarrier products below
         float sigma2 = 0.f;
-        if constexpr (!SC) {
+        if constexpr (!SC && (OPT & kOptNoEstimate) == 0) {
           float sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int m = 0; m < E; ++m) sq[m & 3] = fmaf(u[m].x, u[m].x, fmaf(u[m].y, u[m].y, sq[m & 3]));
@@ -908,7 +910,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           // SC: yv = swap(z~) of time sample k, already equalised and scaled for the slicer
           const float a = SC ? yv.y : fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
           const float b = SC ? -yv.x : fmaf(yv.x, e.y, -yv.y * e.x);  // -Im(Y conj A)
-          const float inv = SC ? 1.0f : fast_rcp(e.z + sigma2);
+          const float inv = SC ? 1.0f : fast_rcp((OPT & kOptNoEstimate) ? e.z : e.z + sigma2);
           if constexpr (DUMP) {
             if (!SC && active && p.dump_y) p.dump_y[s * N + k] = make_float2(yv.x * p.y_scale, yv.y * p.y_scale);
             // 2 (s_k - 1) / knorm_k with knorm_k^2 = 2 (M_k - 1) / 3, M_k = (top + 1)^2

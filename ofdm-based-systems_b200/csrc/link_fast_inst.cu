@@ -119,9 +119,18 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
     }
   }
 #endif
-  if (L->d.n_taps <= 1) return launch_fast_kernel<E, T, false, false, false, false, false, false, 1>(L, p, stream);
-  if (L->d.n_taps <= 4) return launch_fast_kernel<E, T, false, false, false, false, false, false, 4>(L, p, stream);
-  return launch_fast_kernel<E, T, false, false>(L, p, stream);
+  // ZF / no equaliser: sigma2 = 0, so the per-symbol noise estimate of the MMSE form is dropped; one tap: the plain complex
+  // product (4 FFMA) beats the Gauss form (3 FFMA + 3 FADD)
+  constexpr int kZf = kOptDefault | kOptNoEstimate;
+  const bool mmse = L->d.equalizer == OFDM_EQ_MMSE;
+  if (L->d.n_taps <= 1)
+    return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptNoise32>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptNoise32 | kOptNoEstimate>(L, p, stream);
+  if (L->d.n_taps <= 4)
+    return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 4>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, false, false, false, false, 4, S, kZf>(L, p, stream);
+  return mmse ? launch_fast_kernel<E, T, false, false>(L, p, stream)
+              : launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, kZf>(L, p, stream);
 }
 
 }  // namespace ofdm
