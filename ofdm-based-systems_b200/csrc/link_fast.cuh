@@ -623,13 +623,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           }
         }
         [[maybe_unused]] float2 new_tail;
+        [[maybe_unused]] float2 fold[8];   // zero padding shorter than the channel: what overlap-add folds onto samples 0 .. P-1
         if constexpr (ISI) {
           // sample -j before the body (j = 8 - i): inside the cyclic prefix for j <= P (the wrap-around above), else
           // sample N - (j - P) of the previous OFDM symbol
           if (t == 0) {
+            if (p.zero_prefix) {
+              // Zero padding shorter than the channel memory (prefix/models.py:71-101 over channel/models.py:52-55): the
+              // receiver folds only the P tail samples it keeps, fold[i] = sum_{l > i} h_l x[N - (l - i)] for i < P (lane
+              // 0's wrap-around halo IS the symbol's own tail x[N-8 .. N-1]); the rest of the tail leaks into the next
+              // symbol, whose samples -j see zeros for j <= P (the padding) and this symbol's body beyond.
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (8 - i > P) prev[i] = s_tail[i + P];
+              for (int i = 0; i < 8; ++i) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int l = i + 1; l < TAPS; ++l) {
+                  const float2 h = p.taps[l], x = prev[8 - (l - i)];
+                  acc.x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc.x));
+                  acc.y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc.y));
+                }
+                fold[i] = i < P ? acc : make_float2(0.f, 0.f);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) prev[i] = (8 - i > P) ? s_tail[i + P] : make_float2(0.f, 0.f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (8 - i > P) prev[i] = s_tail[i + P];
+            }
           }
           if (t < G::TAIL_F2) new_tail = buf[(T - 1) * RS + (E - 8) + t];   // this symbol's tail, before the FIR overwrites it
         }
@@ -730,6 +751,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             *reinterpret_cast<float4*>(row + 8 * c + i) = make_float4(y[i].x, y[i].y, y[i + 1].x, y[i + 1].y);
 #pragma unroll
           for (int i = 0; i < 8; ++i) prev[i] = cur[i];
+        }
+        if constexpr (ISI) {
+          if (p.zero_prefix && t == 0) {   // the folded part of the symbol's own tail (see above)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) row[i] = cadd(row[i], fold[i]);
+          }
         }
         if constexpr (!REPLAY && NOISE32) {
           if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line

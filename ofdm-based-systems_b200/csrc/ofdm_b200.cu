@@ -486,7 +486,7 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
                           // guard interval at least as long as the channel memory (cyclic or zero-padded), or inter-symbol
                           // interference with a short cyclic prefix / no prefix: one order, chained symbols
                           (P >= Lt - 1 ||   /* a one-tap channel needs no guard interval: "no prefix" is then a cyclic prefix of length 0 */
-                           (desc->prefix_type != OFDM_PREFIX_ZERO && uniform_orders(orders, N) && !amp && !rx_gain)) &&
+                           (uniform_orders(orders, N) && !amp && !rx_gain)) &&
                           P < N && !(force && force[0] == '1');
     L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
     // PSK: one order M = 2 .. 256 on every subcarrier, OFDM, guard interval at least as long as the channel memory

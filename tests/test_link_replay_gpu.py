@@ -43,7 +43,7 @@ def rel_err(a, ref):
 # golden cases whose link shape the register-resident fast kernel covers (csrc/link_fast.cuh)
 FAST_CASES = {"headline_n1024_64qam_mmse", "c2_n1024_16qam_mmse", "c3_n64_64qam_mmse_p2", "c3_n64_64qam_zf_p2",
               "c5_n4096_256qam_mmse", "c1_n64_qpsk_cp16_awgn_zf", "cp10_n64_16qam_mmse", "rawtaps_n64_16qam_mmse", "n512_256qam_zf", "sc_n256_16qam_mmse",
-              "sc_n64_qpsk_zf_p1", "zp_n256_64qam_zf", "zp_n64_16qam_mmse", "isi_cp3_n256_64qam_mmse",
+              "sc_n64_qpsk_zf_p1", "zp_n256_64qam_zf", "zp_n64_16qam_mmse", "isi_zp2_n64_qpsk_mmse", "isi_cp3_n256_64qam_mmse",
               "isi_none_n128_16qam_zf", "psk2_n64_zf_flat", "psk8_n128_mmse_two_ray", "psk16_n64_none_eq_flat", "adaptive_p1_n64_mmse",
               "adaptive_severe_n256_mmse"}
 
