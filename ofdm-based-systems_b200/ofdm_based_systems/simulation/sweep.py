@@ -149,12 +149,15 @@ class LinkSweep:
         return first, base + (1 if rank < rem else 0)
 
     def enqueue(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
-                weak_scaling: bool = False, kernel_events=None):
+                weak_scaling: bool = False, kernel_events=None, overlap_collective: bool = False):
         """Queue the whole sweep on the current CUDA stream - ONE launch of the link kernel with the SNR point as the
         grid's second dimension (ofdm_link_launch_sweep), one launch that packs the per-point counters into the
         all-reduce payload - then ONE all-reduce per sweep; nothing is read back.  Returns the device tensor
         [points, 9 + world] (float64) that ``finalize`` decodes.
-        ``kernel_events``: optional (start, end) torch CUDA events recorded around the link kernel launch."""
+        ``kernel_events``: optional (start, end) torch CUDA events recorded around the link kernel launch.
+        ``overlap_collective``: the all-reduce is issued asynchronously (it runs on the process group's own stream behind
+        this sweep's kernels), so the next sweep's kernel does not wait for the slowest rank of this one; call
+        ``wait_collectives`` (or ``finalize``) before reading any payload."""
         import torch
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized()
@@ -176,12 +179,23 @@ class LinkSweep:
             kernel_events[1].record()
         self.link.pack_sweep(payload.data_ptr(), rank, world, stream)
         if world > 1:
-            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group if distributed else None)
+            work = dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group if distributed else None,
+                                   async_op=overlap_collective)
+            if overlap_collective:
+                self._pending = getattr(self, "_pending", [])
+                self._pending.append(work)
         return payload
+
+    def wait_collectives(self) -> None:
+        """Makes the current stream wait for every all-reduce issued with ``overlap_collective``."""
+        for work in getattr(self, "_pending", []):
+            work.wait()
+        self._pending = []
 
     def finalize(self, snr_dbs: Sequence[float], payload) -> List[dict]:
         """Device -> host read of the combined counters; result keys follow the reference's result dict
         (bit_errors / total_bits / bit_error_rate / symbol_errors / symbol_error_rate / papr_db)."""
+        self.wait_collectives()
         return decode_counters(snr_dbs, payload, self.cfg.num_subcarriers + self.cfg.prefix_length)
 
     def sweep_counters(self, snr_dbs: Sequence[float], n_symbols: int, *, seed: int = 0x0FD3, group=None,
