@@ -27,6 +27,7 @@ struct WaterfillParams {
   double* capacity;      // [F][N] (may be null)
   int n, n_taps, scheme, waterfilling, min_order, max_order, order_rule;
   double noise_power, total_power, gap, tolerance, ser, capacity_scaling;
+  int smem_floors;       // 1: the N floors of the bisection live in dynamic shared memory (N <= 4096), 0: in `power`
 };
 
 __device__ __forceinline__ double block_sum(double x, double* scratch) {
@@ -102,7 +103,10 @@ __global__ void __launch_bounds__(kWfThreads) waterfill_bitload_kernel(const Wat
   const int f = blockIdx.x, n = p.n;
   if (threadIdx.x < p.n_taps) s_taps[threadIdx.x] = p.taps[(size_t)f * p.n_taps + threadIdx.x];
   __syncthreads();
-  double* power = p.power + (size_t)f * n;   // holds the floor during the bisection
+  extern __shared__ double s_floor[];
+  double* power = p.power + (size_t)f * n;
+  // the floors are read ~50 times by the bisection: shared memory when they fit, else the output row holds them
+  double* floors = p.smem_floors ? s_floor : power;
   int* orders = p.orders + (size_t)f * n;
 
   // ---- gains and floors
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(kWfThreads) waterfill_bitload_kernel(const Wat
     if (p.h_eq) p.h_eq[(size_t)f * n + k] = h;
     const double g = h.x * h.x + h.y * h.y;
     const double fl = p.noise_power / (g * n);
-    power[k] = fl;
+    floors[k] = fl;
     max_floor = fmax(max_floor, fl);
   }
   __syncthreads();
@@ -126,19 +130,19 @@ __global__ void __launch_bounds__(kWfThreads) waterfill_bitload_kernel(const Wat
     for (iters = 1; iters <= 100; ++iters) {
       mu = (lo + hi) / 2;
       double s = 0.0;
-      for (int k = threadIdx.x; k < n; k += kWfThreads) s += fmax(0.0, mu - power[k]);
+      for (int k = threadIdx.x; k < n; k += kWfThreads) s += fmax(0.0, mu - floors[k]);
       s = block_sum(s, scratch);
       if (fabs(s - p.total_power) < p.tolerance) break;
       if (s < p.total_power) lo = mu; else hi = mu;
     }
     if (iters > 100) iters = 100;
     double s = 0.0;
-    for (int k = threadIdx.x; k < n; k += kWfThreads) s += fmax(0.0, mu - power[k]);
+    for (int k = threadIdx.x; k < n; k += kWfThreads) s += fmax(0.0, mu - floors[k]);
     s = block_sum(s, scratch);
     const double scale = s > 0.0 ? p.total_power / s : 1.0;
     double lvl = 0.0, cnt = 0.0;
     for (int k = threadIdx.x; k < n; k += kWfThreads) {
-      const double fl = power[k];
+      const double fl = floors[k];
       const double pk = fmax(0.0, mu - fl) * scale;
       power[k] = pk;
       const double2 h = channel_response(s_taps, p.n_taps, k, n);
@@ -201,7 +205,9 @@ int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* d, const doubl
   p.gap = d->gap;
   p.tolerance = d->tolerance > 0 ? d->tolerance : 1e-8;
   p.ser = 0.0;
-  waterfill_bitload_kernel<<<(unsigned)n_realisations, kWfThreads, 0, (cudaStream_t)stream>>>(p);
+  p.smem_floors = d->n_subcarriers <= 4096 ? 1 : 0;    // 32 KB of doubles: inside the 48 KB every kernel may use without opting in
+  waterfill_bitload_kernel<<<(unsigned)n_realisations, kWfThreads, p.smem_floors ? size_t(d->n_subcarriers) * sizeof(double) : 0,
+                             (cudaStream_t)stream>>>(p);
   count_launch();
   CUDA_TRY(cudaGetLastError());
   return OFDM_OK;
