@@ -203,7 +203,8 @@ def run_reference_arm(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bits/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "step": f"{per_step} x {n_ofdm} OFDM symbols on {cores} host processes"},
+            "config": {"workload": WORKLOAD},
+            "step_sample": f"{per_step} x {n_ofdm} OFDM symbols on {cores} host processes per step (a bounded sample of the workload)",
             "cpu_baseline": {"value": value, "unit": "bits/s", "cores": cores, "kind": kind,
                              "sample": f"{args.steps} steps x {per_step} chunks x {n_ofdm} OFDM symbols cycling through the SNR grid, {what}"},
             "e2e": {"value": value, "unit": "bits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

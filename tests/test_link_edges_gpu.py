@@ -203,3 +203,25 @@ def test_every_variant_is_deterministic_and_additive(v, kat):
     assert a.bit_errors + b.bit_errors == runs[0].bit_errors and a.symbol_errors + b.symbol_errors == runs[0].symbol_errors
     assert max(a.tx_power_max, b.tx_power_max) == runs[0].tx_power_max
     link.close()
+
+
+def test_two_devices_in_one_process(kat):
+    """The dynamic-shared-memory opt-in and the occupancy are per device: links on device 0 and device 1 of ONE process run
+    the same shapes (N = 1024 needs 164 KB of shared memory per block) and return identical counters."""
+    from ofdm_based_systems import _native
+    if _native.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    taps = kat["chan_severe_multipath"]
+    taps_n = taps / np.sqrt(np.sum(np.abs(taps) ** 2))
+    out = []
+    for dev in (0, 1, 0):
+        for n, order in ((1024, 64), (256, 16), (8192, 16)):
+            link = _native.Link(n, taps_n, np.fft.fft(taps, n), np.full(n, order), prefix_type="CYCLIC", prefix_len=7,
+                                equalizer="MMSE", device=dev)
+            r = link.run_fused(18.0, 0.089, 300, seed=9)
+            link.close()
+            out.append((dev, n, r.bit_errors, r.bits))
+    per_shape = {}
+    for dev, n, be, bits in out:
+        per_shape.setdefault(n, set()).add((be, bits))
+    assert all(len(v) == 1 for v in per_shape.values()), out
