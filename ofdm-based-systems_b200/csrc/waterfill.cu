@@ -168,6 +168,94 @@ __global__ void __launch_bounds__(kWfThreads) waterfill_bitload_kernel(const Wat
   if (threadIdx.x == 0 && p.iterations) p.iterations[f] = iters;
 }
 
+// Narrow links (N <= 128, the reference's shipped configurations are N = 64): ONE WARP per channel realisation, the
+// floors in registers, warp shuffles instead of block barriers - the block-per-realisation kernel above spends its time in
+// the two __syncthreads of each of the ~50 bisection steps with 192 of its 256 threads idle.  Same arithmetic per
+// subcarrier and the same bisection; only the order of the additions inside the sums differs.
+constexpr int kWfWarpJ = 4;   // subcarriers per lane
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+  return x;
+}
+__global__ void __launch_bounds__(kWfThreads) waterfill_bitload_warp_kernel(const WaterfillParams p, long long n_frames) {
+  __shared__ double2 s_taps[kWfThreads / 32][kMaxTaps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n = p.n;
+  const long long f = (long long)blockIdx.x * (kWfThreads / 32) + w;
+  if (f >= n_frames) return;            // whole warps leave: no block-wide barrier below
+  for (int l = lane; l < p.n_taps; l += 32) s_taps[w][l] = p.taps[(size_t)f * p.n_taps + l];
+  __syncwarp();
+  double* power = p.power + (size_t)f * n;
+  int* orders = p.orders + (size_t)f * n;
+  double fl[kWfWarpJ], g[kWfWarpJ];
+  double max_floor = 0.0;
+#pragma unroll
+  for (int j = 0; j < kWfWarpJ; ++j) {
+    const int k = lane + 32 * j;
+    fl[j] = 0.0;
+    g[j] = 1.0;
+    if (k < n) {
+      const double2 h = channel_response(s_taps[w], p.n_taps, k, n);
+      if (p.h_eq) p.h_eq[(size_t)f * n + k] = h;
+      g[j] = h.x * h.x + h.y * h.y;
+      fl[j] = p.noise_power / (g[j] * n);
+      max_floor = fmax(max_floor, fl[j]);
+    }
+  }
+  double mu = 0.0;
+  int iters = 0;
+  if (p.waterfilling) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) max_floor = fmax(max_floor, __shfl_xor_sync(0xffffffffu, max_floor, off));
+    auto filled = [&](double level) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < kWfWarpJ; ++j)
+        if (lane + 32 * j < n) s += fmax(0.0, level - fl[j]);
+      return warp_sum(s);
+    };
+    double lo = 0.0, hi = p.total_power + max_floor;
+    mu = (lo + hi) / 2;
+    for (iters = 1; iters <= 100; ++iters) {
+      mu = (lo + hi) / 2;
+      const double s = filled(mu);
+      if (fabs(s - p.total_power) < p.tolerance) break;
+      if (s < p.total_power) lo = mu; else hi = mu;
+    }
+    if (iters > 100) iters = 100;
+    const double s = filled(mu);
+    const double scale = s > 0.0 ? p.total_power / s : 1.0;
+    double lvl = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int j = 0; j < kWfWarpJ; ++j) {
+      const int k = lane + 32 * j;
+      if (k < n) {
+        const double pk = fmax(0.0, mu - fl[j]) * scale;
+        power[k] = pk;
+        if (pk > 1e-10) { lvl += pk + p.noise_power / g[j]; cnt += 1.0; }
+        orders[k] = gap_rule_order(pk * g[j] / p.noise_power, p);
+        if (p.capacity) p.capacity[(size_t)f * n + k] = log2(1.0 + pk * g[j] / p.noise_power + 1e-12);
+      }
+    }
+    lvl = warp_sum(lvl);
+    cnt = warp_sum(cnt);
+    if (lane == 0) p.water_level[f] = cnt > 0.0 ? lvl / cnt : nan("");
+  } else {
+    const double pk = p.total_power / n;   // UniformPowerAllocation (power_allocation/models.py:61-69)
+#pragma unroll
+    for (int j = 0; j < kWfWarpJ; ++j) {
+      const int k = lane + 32 * j;
+      if (k < n) {
+        power[k] = pk;
+        orders[k] = gap_rule_order(pk * g[j] / p.noise_power, p);
+        if (p.capacity) p.capacity[(size_t)f * n + k] = log2(1.0 + pk * g[j] / p.noise_power + 1e-12);
+      }
+    }
+    if (lane == 0) p.water_level[f] = nan("");
+  }
+  if (lane == 0 && p.iterations) p.iterations[f] = iters;
+}
+
 }  // namespace ofdm
 
 using namespace ofdm;
@@ -206,8 +294,13 @@ int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* d, const doubl
   p.tolerance = d->tolerance > 0 ? d->tolerance : 1e-8;
   p.ser = 0.0;
   p.smem_floors = d->n_subcarriers <= 4096 ? 1 : 0;    // 32 KB of doubles: inside the 48 KB every kernel may use without opting in
-  waterfill_bitload_kernel<<<(unsigned)n_realisations, kWfThreads, p.smem_floors ? size_t(d->n_subcarriers) * sizeof(double) : 0,
-                             (cudaStream_t)stream>>>(p);
+  if (d->n_subcarriers <= 32 * kWfWarpJ) {
+    const long long per_block = kWfThreads / 32;
+    waterfill_bitload_warp_kernel<<<(unsigned)((n_realisations + per_block - 1) / per_block), kWfThreads, 0, (cudaStream_t)stream>>>(p, n_realisations);
+  } else {
+    waterfill_bitload_kernel<<<(unsigned)n_realisations, kWfThreads, p.smem_floors ? size_t(d->n_subcarriers) * sizeof(double) : 0,
+                               (cudaStream_t)stream>>>(p);
+  }
   count_launch();
   CUDA_TRY(cudaGetLastError());
   return OFDM_OK;

@@ -93,3 +93,23 @@ def test_null_channels_are_refused_like_the_reference():
         _native.run_frames(64, 2, 10, 10.0, taps=np.array([[1.0, 0.5], [0.0, 0.0]], complex), order=16)
     with pytest.raises(ValueError, match="All channel gains must be positive"):
         _native.waterfill_bitload_batched(np.array([[1.0, -1.0]], complex), 64, 10.0)     # H[0] = 0
+
+
+@pytest.mark.parametrize("n", [8, 64, 128])
+def test_narrow_links_one_warp_per_realisation(n):
+    """N <= 128 runs one warp per channel realisation (8 per block; 37 realisations leave the last block partly empty)."""
+    from ofdm_based_systems._native import waterfill_bitload_batched
+    rng = np.random.default_rng(7 + n)
+    f, l = 37, 4
+    taps = (rng.normal(size=(f, l)) + 1j * rng.normal(size=(f, l))) * np.sqrt(np.exp(-np.arange(l) / 2))
+    for wf in (True, False):
+        out = waterfill_bitload_batched(taps, n, 15.0, waterfilling=wf)
+        mism = 0
+        for i in range(f):
+            orders, power, level = oc.adaptive_setup(n, taps[i], 15.0, 1e-3, "QAM", waterfill=wf)
+            np.testing.assert_allclose(out["power"][i], power, rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(out["h_eq"][i], np.fft.fft(taps[i], n), rtol=0, atol=1e-12)
+            mism += int(np.sum(out["orders"][i] != orders))
+            if wf:
+                assert abs(out["water_level"][i] - level) < 1e-6 * abs(level)
+        assert mism <= 1
