@@ -14,7 +14,7 @@
 
 #include "link_fast.cuh"
 #ifdef WITH_STREAM_EXPERIMENT
-#include "experiments/link_stream_kernel.cuh"
+#include "experiments/link_stream2_kernel.cuh"
 #endif
 
 using namespace ofdm;
@@ -109,9 +109,20 @@ int main(int argc, char** argv) {
   if (!only || strstr(name, only))                                                                      \
     run(name, ofdm_link_fast_kernel<E, T, false, true, false, BLOCK, SYNC, A, F, S, I, K, NR, FU, TAPS, OPT, ##__VA_ARGS__>, BLOCK, \
         FastGeometry<E, T, BLOCK>::SMEM_BYTES, p, d_cnt, reps, points);
+#ifdef WITH_STREAM_EXPERIMENT
 #define VARIANT2(name, BLOCK, TAPS, TRIG)                                                                \
   if (!only || strstr(name, only))                                                                      \
     run(name, ofdm_link_stream_kernel<E, T, BLOCK, false, false, TAPS, TRIG>, BLOCK, StreamGeometry<E, T, BLOCK>::SMEM_BYTES, p, d_cnt, reps, points);
+#else
+#define VARIANT2(name, BLOCK, TAPS, TRIG)
+#endif
+#ifdef WITH_STREAM_EXPERIMENT
+#define VARIANT3(name, MODE)                                                                             \
+  if (!only || strstr(name, only))                                                                      \
+    run(name, ofdm_link_stream2_kernel<E, T, 512, MODE, 8>, 512, StreamGeometry<E, T, 512>::SMEM_BYTES + (((MODE) & 10) == 10 ? 32768 : 0), p, d_cnt, reps, points);
+#else
+#define VARIANT3(name, MODE)
+#endif
 #include "fast_variants.inc"
   return 0;
 }
