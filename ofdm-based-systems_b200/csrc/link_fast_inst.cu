@@ -98,7 +98,11 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   if (adapt) OFDM_FAST_VARIANT(true, false, false, false);     // per-subcarrier orders / applied power loading
 #undef OFDM_FAST_VARIANT
   if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
-  if (dump) return launch_fast_kernel<E, T, true, false>(L, p, stream);
+  // the dump-capable kernel evaluates the FIR in the same form as the counters-only kernel of the link (plain complex
+  // product for one tap, Gauss form otherwise), so that the two return identical counters
+  if (dump)
+    return L->d.n_taps <= 1 ? launch_fast_kernel<E, T, true, false, false, false, false, false, 1, 0, kOptNoise32>(L, p, stream)
+                            : launch_fast_kernel<E, T, true, false>(L, p, stream);
   // The warps of a block run free (SYNC = 0).  Round 1 aligned the warps that share a scheduler at the section
   // boundaries (named barrier per scheduler, SYNC = 2): they then share instruction fetches (stall_no_instruction 0.16
   // instead of 0.49 per issue) but meet the shared-memory exchanges and the MUFU section together.  With the round-2

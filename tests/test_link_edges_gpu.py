@@ -114,6 +114,12 @@ VARIANTS = [
     ("four_taps", 64, 64, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "OFDM", False),
     ("four_taps_256", 256, 16, "QAM", "default_multipath", "CYCLIC", 3, "ZF", "OFDM", False),
     ("sc_isi", 512, 16, "QAM", "severe_multipath", "CYCLIC", 3, "MMSE", "SC-OFDM", False),
+    # the instantiations without the per-symbol noise estimate (ZF / no equaliser) at 8 taps, the one-tap MMSE one, and
+    # zero padding shorter than the channel (partial overlap-add + leak into the next symbol), OFDM and SC-OFDM
+    ("zf8", 1024, 64, "QAM", "severe_multipath", "CYCLIC", 7, "ZF", "OFDM", False),
+    ("flat_mmse", 256, 64, "QAM", "flat_fading", "CYCLIC", 4, "MMSE", "OFDM", False),
+    ("isi_zp", 256, 64, "QAM", "severe_multipath", "ZERO", 3, "MMSE", "OFDM", False),
+    ("isi_zp_sc", 128, 4, "QAM", "Lin-Phoong_P2", "ZERO", 1, "MMSE", "SC-OFDM", False),
 ]
 
 
