@@ -43,6 +43,15 @@ orders = rng.choice([0, 4, 16, 64, 256], size=1024)
 exercise(link(1024, 0, "rayleigh_fading", "CYCLIC", 5, "MMSE", orders=orders), 1024, 5, 0)
 exercise(link(64, 16, "severe_multipath", "CYCLIC", 40, "MMSE"), 64, 40, 4)                    # long prefix
 exercise(link(32, 16, "two_ray", "ZERO", 1, "MMSE"), 32, 1, 4)                                 # general kernel
+exercise(link(256, 64, "severe_multipath", "ZERO", 3, "MMSE"), 256, 3, 6, n_sym=9)             # zero padding shorter than the channel
+exercise(link(128, 4, "Lin-Phoong_P2", "ZERO", 1, "MMSE", modulator="SC-OFDM"), 128, 1, 2, n_sym=9)
+exercise(link(64, 4, "flat_fading", "CYCLIC", 16, "ZF"), 64, 16, 2)                            # one tap, no noise estimate
+exercise(link(1024, 64, "severe_multipath", "CYCLIC", 7, "ZF"), 1024, 7, 6)
+pl = link(64, 64, "Lin-Phoong_P2", "CYCLIC", 3, "MMSE", amp=np.full(64, 0.125), rx_gain=np.full(64, 8.0))   # post-equaliser stage
+res = pl.run_fused_renormalised(20.0, 0.0, 50, noise_profile=np.linspace(1.0, 2.0, 64), seed=3)
+print("post ok", res.bits, res.bit_errors)
+pl.close()
+w8 = nat.waterfill_bitload_batched(np.tile(kat["chan_severe_multipath"][None, :], (11, 1)), 64, 15.0)   # one warp per realisation
 out = nat.run_frames(256, 6, 20, 18.0, n_taps=8, waterfilling=True)
 out = nat.run_frames(4096, 3, 9, 18.0, n_taps=8, order=64)
 w = nat.waterfill_bitload_batched(kat["chan_severe_multipath"][None, :], 256, 15.0)
