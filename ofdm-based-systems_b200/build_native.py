@@ -26,8 +26,8 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-diag-suppress", "177",
               # ~200 kernel instantiations with line tables: zstd-compressed fatbins keep the library near 10 MB
               "--compress-mode=size"]
-if os.environ.get("OFDM_FAST_EXPERIMENTS"):        # extra instantiations of the headline kernel for A/B timing
-    NVCC_FLAGS.append("-DOFDM_FAST_EXPERIMENTS")
+if os.environ.get("OFDM_FAST_PHILOX_ROUNDS"):      # 10: the Random123 default instead of the crush-resistant minimum (7)
+    NVCC_FLAGS.append("-DOFDM_FAST_PHILOX_ROUNDS=" + str(int(os.environ["OFDM_FAST_PHILOX_ROUNDS"])))
 
 
 def _nvcc() -> str:

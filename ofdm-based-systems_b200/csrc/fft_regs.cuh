@@ -155,12 +155,15 @@ __device__ __forceinline__ void dit_butterfly(float2& a, float2& c) {
 
 // In-place decimation-in-time FFT of R points in registers.  Same convention as fft_dif_inplace: input
 // element n in v[n], output element k in v[fft_out_index<R>(k)] (working slot j lives in v[brev j]).
-template <int R, int DIR>
+// FIRST = 1 skips the first stage (the trivial butterflies of elements n and n + R/2, n < R/2, in place): callers that
+// can fuse work into those butterflies - a run-time twiddle per element, a common offset - do them themselves.
+template <int R, int DIR, int FIRST = 0>
 __device__ __forceinline__ void fft_dit_inplace(float2 (&v)[R]) {
   static_assert((R & (R - 1)) == 0 && R >= 1, "radix must be a power of two");
   constexpr int LOG = cx_log2(R);
-  static_for<LOG>([&](auto S) {
-    constexpr int half = 1 << decltype(S)::value;
+  static_for<LOG - FIRST>([&](auto S0) {
+    constexpr int S = decltype(S0)::value + FIRST;
+    constexpr int half = 1 << S;
     constexpr int span = 2 * half;
     static_for<R / span>([&](auto B) {
       static_for<half>([&](auto I) {

@@ -33,10 +33,12 @@ int launch_fast_frames(int n_subcarriers, int sms, const FastParams& p, cudaStre
 std::vector<float2> build_fast_twiddles(int N) {
   const int E = fast_samples_per_lane(N), T = N / E, W = T / E, RS = E + 2;
   std::vector<float2> tw(size_t(E) * RS, make_float2(0.f, 0.f));
+  // row k (lane column): the pairs {W^(k n), W^(k (n + E/2))}, n < E/2, W = exp(-2 pi i / E^2) - one 128-bit load per
+  // first-stage butterfly of the second codelet (kOptFusedTwiddle in link_fast.cuh)
   for (int k = 0; k < E; ++k)
-    for (int r = 1; r < E; ++r) {
+    for (int r = 0; r < E; ++r) {
       const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
-      tw[size_t(k) * RS + r - 1] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      tw[size_t(k) * RS + 2 * (r % (E / 2)) + r / (E / 2)] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
   if (W > 1)
     for (int j = 0; j < N / W; ++j) {

@@ -51,7 +51,8 @@ struct FastParams {
   float2 taps[kFastTaps];   // unit-energy taps / (sqrt(2(M-1)/3) * sqrt(N))   (levels are 2c-(s-1), IFFT unscaled)
   float4 taps3[kFastTaps];  // the same taps as {h_re, h_im - h_re, h_re + h_im, -}: three real products per complex one
   const float4* eq_tab;     // {Re A, Im A, G, -}: decision = sat(Re/Im(Y~ conj A) / (G + sigma2) + 0.5) * (s-1)
-  const float2* tw;         // pass-2 twiddles exp(-2 pi i k r / E^2) at [k*(E+2) + r-1], then (T > E) the pass-3 base
+  const float2* tw;         // pass-2 twiddles exp(-2 pi i k r / E^2) at [k*(E+2) + r-1] (kOptFusedTwiddle: r = n at [k*(E+2) + 2n],
+                            // r = n + E/2 at [k*(E+2) + 2n + 1], n < E/2), then (T > E) the pass-3 base
                             // twiddles exp(-2 pi i j / N), j < N / (T/E)   (build_fast_twiddles, link_fast.cu)
   float slice_top;          // s-1
   float tx_scale2;          // |tx|^2 = tx_scale2 * |x~|^2 (PAPR statistics)
@@ -61,6 +62,7 @@ struct FastParams {
   int equalizer;
   int half_bits;            // log2(s)
   unsigned int field_mask;  // (s-1) << 1 replicated in every byte
+  unsigned int k4b = 0x4B000000u;   // bits of 2^23, read from the constant bank so that PRMT keeps its byte selector as the immediate
   unsigned long long seed;
   unsigned int point;
   // n_points >= 1 SNR points in one grid: the blocks with blockIdx.y = pt run point `point + pt` with point_tab[pt] and
@@ -162,6 +164,24 @@ __device__ __forceinline__ float fast_lg2(float x) {
   return y;
 }
 
+template <bool V>
+__device__ __forceinline__ float4 lds128(const float2* ptr) {
+  if constexpr (V) {
+    float4 r;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(ptr)));
+    return r;
+  } else {
+    return *reinterpret_cast<const float4*>(ptr);
+  }
+}
+__device__ __forceinline__ float2 lds64v(const float2* ptr) {
+  float2 r;
+  asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"((unsigned)__cvta_generic_to_shared(ptr)));
+  return r;
+}
+
 // circularly-symmetric sigma * (N(0,1) + j N(0,1)) from two 32-bit words (same distribution as box_muller())
 __device__ __forceinline__ float2 fast_box_muller(uint32_t wr, uint32_t wa, float sigma) {
   const float u1 = fmaf((float)wr, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
@@ -189,16 +209,19 @@ __device__ __forceinline__ float2 fast_noise(uint32_t wr, uint32_t wa, uint32_t 
 //   angle = 2 pi (a + 0.5) / 4096 - pi via the mantissa of 2^23 + a: 4096 equally spaced rays are invisible after any
 //   projection (the radius is continuous) and noise is rotation invariant.
 constexpr uint32_t kRefillBelow = 4096u;   // w < 4096  <=>  radius field == 0
+template <bool WORD = false>
 __device__ __forceinline__ float noise20_radius(uint32_t w, float c2, float c2m) {
-  return fast_sqrt(fmaf(c2, fast_lg2((float)(w | 0xFFFu)), c2m));
+  // WORD: u = w 2^-32 straight from the word (the angle field only moves u inside its 2^-20 cell)
+  return fast_sqrt(fmaf(c2, fast_lg2((float)(WORD ? w : (w | 0xFFFu))), c2m));
 }
 __device__ __forceinline__ float2 noise20_dir(uint32_t w) {
   const float f = __uint_as_float((w & 0xFFFu) | 0x4B000000u);                                   // 2^23 + a
   const float ang = fmaf(f, 1.5339807878856412e-03f, -12871.104692850697f);                      // (2 pi / 4096)(a + 0.5) - pi (offset for the ROUNDED slope)
   return make_float2(__cosf(ang), __sinf(ang));
 }
+template <bool WORD = false>
 __device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m) {
-  const float rad = noise20_radius(w, c2, c2m);
+  const float rad = noise20_radius<WORD>(w, c2, c2m);
   const float2 d = noise20_dir(w);
   return make_float2(rad * d.x, rad * d.y);
 }
@@ -206,7 +229,7 @@ __device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m) 
 // Rare path of the 32-bit-per-sample noise: at least one of this lane's E radius fields was 0.  Regenerates the lane's
 // words, and for every sample with a zero field draws 32 fresh bits r: u = (r + 0.5) 2^-52, same direction; the FIR
 // output in `row` already holds the coarse sample, so the difference is added.
-template <int E, int NROUNDS>
+template <int E, int NROUNDS, bool WORD = false>
 __device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, uint32_t gs_hi, uint32_t point, PhiloxKey key,
                                           float c2, float c2m, float2* dump_noise, unsigned long long dump_base) {
 #pragma unroll 1
@@ -223,7 +246,7 @@ __device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, ui
         const uint4 r = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (1u << 20) | uint32_t(E * t + i), point), key);
         const float u = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r + 0.5) 2^-32
         const float rad_new = fast_sqrt(c2 * (fast_lg2(u) - 20.0f));
-        const float rad_old = noise20_radius(w, c2, c2m);
+        const float rad_old = noise20_radius<WORD>(w, c2, c2m);
         const float2 d = noise20_dir(w);
         const float2 o = row[i];
         row[i] = make_float2(fmaf(rad_new - rad_old, d.x, o.x), fmaf(rad_new - rad_old, d.y, o.y));
@@ -258,16 +281,55 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 //   2  FIR with three real products per complex tap (Gauss) instead of four
 //   4  no per-symbol noise estimate: ZF / no equaliser, where sigma2 = 0 (the MMSE form then needs neither the power sum
 //      over the spectrum nor its shuffles; -3 instructions per subcarrier)
-constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptNoEstimate = 4, kOptDefault = 3;
+//   16..240  depth of the twiddle ring of the transform's exchange (bits 4..7; 0 = load each pair at its use)
+//   512  transmitted labels kept as ONE packed word per 4 subcarriers (column index in the low nibble of a byte, row
+//        index in the high nibble) instead of one word per axis: 8 fewer live registers at N = 1024 and half the words
+//        for the error count
+//   1024 pass-2 twiddles fused into the first butterflies of the second codelet: (a, c) <- (w_a a + w_c c, w_a a - w_c c)
+//        costs 10 instructions instead of 12 (table layout: FastParams::tw)
+//   2048 level offset -(s-1) folded into the first butterflies of the transmitter's first codelet: the difference of two
+//        2^23-based label floats needs no offset, their sum one (6 FADD per butterfly instead of 8)
+//   4096 noise radius from the whole 32-bit word, lg2(float(w)), without masking the angle field out first
+//   8192 PAPR maximum with 3-input integer maxima on the bit patterns (non-negative floats order like integers)
+//   16384 the data-bit Philox calls use NROUNDS like the noise calls
+//   32768 Gauss-form FIR without the two final additions: the k3 and k2 sums continue the k1 chain,
+//         y_re = k1 - sum (h_re + h_im) x_im, y_im = k1 + sum (h_im - h_re) x_re
+//   65536 error count on ONE word per 4 subcarriers: the column and row difference fields side by side in a byte
+//         ((dc >> 1) | (dr << 3)), inverse Gray code with nibble-isolating masks
+constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptNoEstimate = 4, kOptPackedLabels = 512, kOptFusedTwiddle = 1024,
+              kOptFusedLevels = 2048, kOptRadiusWord = 4096, kOptIntMax = 8192, kOptDataRounds = 16384, kOptFirChain = 32768, kOptJointGray = 65536;
+constexpr int kOptTwRing4 = (4 << 4) | 256;   // twiddle ring of 4 buffers, volatile loads
+// what every product instantiation uses (the twiddle table of a link is laid out for kOptFusedTwiddle), the one-tap and the
+// multi-tap formulation of the channel; profiles/r2_fast_kernel_history.md section 7 has the measurements, the A/B harness
+// (tools/microbench/fast_variants.cu) still builds the formulations without them
+constexpr int kOptCommon = kOptFusedTwiddle | kOptFusedLevels | kOptRadiusWord | kOptIntMax | kOptDataRounds | kOptFirChain |
+                           kOptJointGray | kOptTwRing4;
+constexpr int kOptOneTap = kOptNoise32 | kOptCommon, kOptDefault = kOptNoise32 | kOptGaussFir | kOptCommon;
+
+// Philox4x32 rounds of the fast kernel's bit and noise streams.  7 is the fewest rounds with which Philox4x32 passes
+// BigCrush (Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11, table 2: "crush-resistant");
+// 10 is that paper's default with a safety margin (-DOFDM_FAST_PHILOX_ROUNDS=10 builds the library with it; the general
+// kernel always uses 10).  Three rounds fewer are 2.5 % of the headline kernel's time.
+#ifndef OFDM_FAST_PHILOX_ROUNDS
+#define OFDM_FAST_PHILOX_ROUNDS 7
+#endif
+constexpr int kFastRounds = OFDM_FAST_PHILOX_ROUNDS;
 
 template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 512, int SYNC = 2, bool ADAPT = false,
-          bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = 10, int FIR_UNROLL = 2,
+          bool FRAMES = false, bool SC = false, bool ISI = false, bool PSK = false, int NROUNDS = kFastRounds, int FIR_UNROLL = 2,
           int TAPS = kFastTaps, int OPT = kOptDefault, int MINB = 1>
 __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
   // MINB: blocks per SM the register allocation must allow (2 for the narrow codelets: 64 registers, 32 warps per SM)
   // TAPS: channel taps the FIR evaluates (the host zero-pads the tap table, so a shorter loop only drops exact zeros)
   static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || (!ISI && !FRAMES)), "tap count");
   constexpr bool NOISE32 = (OPT & kOptNoise32) != 0, GAUSS = (OPT & kOptGaussFir) != 0;
+  constexpr int TWR = (OPT >> 4) & 15;        // depth of the twiddle ring of the exchange (0: load at use)
+  constexpr bool PACKED = (OPT & kOptPackedLabels) != 0 && !PSK;   // see kOptPackedLabels
+  constexpr bool FTW = (OPT & kOptFusedTwiddle) != 0;                             // see kOptFusedTwiddle
+  constexpr bool FLV = (OPT & kOptFusedLevels) != 0 && !ADAPT && !PSK && !SC;     // see kOptFusedLevels
+  constexpr bool RWORD = (OPT & kOptRadiusWord) != 0, IMAX = (OPT & kOptIntMax) != 0;
+  constexpr int DROUNDS = (OPT & kOptDataRounds) ? NROUNDS : 10;
+  constexpr bool TWV = (OPT & 256) != 0;       // ring and column loads as volatile accesses (keeps their order in SASS)
   // PSK: M-ary phase-shift keying, one order on every subcarrier; labels through a shared-memory point table at the
   // transmitter, angle rounding at the receiver (the equaliser's positive real denominator does not move the angle)
   static_assert(!PSK || (!ADAPT && !FRAMES && !SC && !ISI), "PSK: one order, single link, OFDM, no ISI");
@@ -474,12 +536,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
     const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
 
     unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1..4 of each byte
+    [[maybe_unused]] unsigned txp[PACKED ? WORDS : 1];   // PACKED: column | row << 4 per byte; txc / txr die after the mapper
     float2 v[E];
 
     // ---- transmitter epilogue: PAPR statistics of the time samples x[t + T m] = sample(m) and their publication
     //      in shared memory for the FIR (prefix/models.py:34-44, simulation/models.py:519-524)
     auto tx_epilogue = [&](auto&& sample) {
         float ssum[4] = {0.f, 0.f, 0.f, 0.f}, smax[4] = {0.f, 0.f, 0.f, 0.f};   // 4 chains: latency, not issue
+        [[maybe_unused]] unsigned imax[2] = {0u, 0u};
+        [[maybe_unused]] float pw_prev = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           const float2 x = sample(m);
@@ -487,10 +552,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             const float pw = fmaf(x.x, x.x, x.y * x.y);
             // the cyclic prefix repeats the last P samples; for P <= T: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
             ssum[m & 3] += (m == E - 1 && t >= T - Pc) ? 2.f * pw : pw;
-            smax[m & 3] = fmaxf(smax[m & 3], pw);
+            if constexpr (IMAX) {
+              if (m & 1) imax[(m >> 1) & 1] = __vimax3_u32(imax[(m >> 1) & 1], __float_as_uint(pw_prev), __float_as_uint(pw));
+              pw_prev = pw;
+            } else {
+              smax[m & 3] = fmaxf(smax[m & 3], pw);
+            }
           }
           col[W * RS * m] = x;
         }
+        if constexpr (PAPR && IMAX) smax[0] = __uint_as_float(max(imax[0], imax[1]));
         if (PAPR && Pc > T) {
           // long prefix (more than one row of samples): the rows above the last one that it also repeats; rolled
           // loop over this lane's own samples in shared memory (rare shape, keeps the instruction stream small)
@@ -562,13 +633,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
               const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
               txc[j] = (txc[j] ^ (txc[j] >> 1)) & fm;
               txr[j] = (txr[j] ^ (txr[j] >> 1)) & fm;
+              if constexpr (PACKED) txp[j] = (txc[j] >> 1) | (txr[j] << 3);
             }
           }
           tsync();
         } else {
 #pragma unroll
           for (int c = 0; c < CALLS; ++c) {
-            const uint4 w = philox4x32<10>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), point), key);
+            const uint4 w = philox4x32<DROUNDS>(make_uint4(gs_lo, gs_hi, (0u << 28) | uint32_t(c * T + t), point), key);
             const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -580,6 +652,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
                 } else {
                   txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
                   txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
+                  if constexpr (PACKED) txp[4 * c + j] = ww[j] & ((fm >> 1) | (fm << 3));
                 }
               }
             }
@@ -595,8 +668,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             v[m] = make_float2(pt.y, pt.x);
           }
         }
+        if constexpr (FLV) {
+          // first butterflies of the codelet on the raw label floats f = 2^23 + 2 index (exact sums and differences):
+          // (v[n], v[n + E/2]) <- (v[n] + v[n + E/2], v[n] - v[n + E/2]) with v = (-(f_r + cen), f_c + cen)
+          // cen2 = -2 (2^23 + s-1): every partial sum below is an even integer below 2^25, hence exact
+          const float cen2 = 2.f * cen, ncen2 = -cen2;
+          const unsigned k4b = p.k4b;
 #pragma unroll
-        for (int m = 0; m < (PSK ? 0 : E); ++m) {
+          for (int n = 0; n < E / 2; ++n) {
+            const int m2 = n + E / 2;
+            const float fca = __uint_as_float(__byte_perm(txc[n >> 2], k4b, 0x7650 + (n & 3)));
+            const float fra = __uint_as_float(__byte_perm(txr[n >> 2], k4b, 0x7650 + (n & 3)));
+            const float fcc = __uint_as_float(__byte_perm(txc[m2 >> 2], k4b, 0x7650 + (m2 & 3)));
+            const float frc = __uint_as_float(__byte_perm(txr[m2 >> 2], k4b, 0x7650 + (m2 & 3)));
+            v[n] = make_float2((ncen2 - fra) - frc, (fca + cen2) + fcc);
+            v[m2] = make_float2(frc - fra, fca - fcc);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < ((PSK || FLV) ? 0 : E); ++m) {
           const unsigned fc = __byte_perm(txc[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
           const unsigned fr = __byte_perm(txr[m >> 2], 0x4B000000u, 0x7650 + (m & 3));
           if constexpr (ADAPT) {
@@ -688,8 +778,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
                 const float xs = (i - l >= 0) ? cs[i - l] : ps[8 + i - l];
                 const float4 h = FRAMES ? s_hdr.taps3[l] : p.taps3[l];
                 k1 = fmaf(h.x, xs, k1);
-                k2 = fmaf(h.y, x.x, k2);
-                k3 = fmaf(h.z, x.y, k3);
+                if constexpr ((OPT & kOptFirChain) == 0) {
+                  k2 = fmaf(h.y, x.x, k2);
+                  k3 = fmaf(h.z, x.y, k3);
+                }
+              }
+              if constexpr ((OPT & kOptFirChain) != 0) {
+                k2 = k3 = k1;
+#pragma unroll
+                for (int l = 0; l < TAPS; ++l) {
+                  const float2 x = (i - l >= 0) ? cur[i - l] : prev[8 + i - l];
+                  const float4 h = FRAMES ? s_hdr.taps3[l] : p.taps3[l];
+                  k2 = fmaf(h.y, x.x, k2);
+                  k3 = fmaf(-h.z, x.y, k3);
+                }
+                y[i] = make_float2(k3, k2);
+                continue;
               }
               y[i] = make_float2(k1 - k3, k1 + k2);
             }
@@ -722,7 +826,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
               wmin = min(min(wmin, min(w8[0], w8[1])), min(min(w8[2], w8[3]), min(min(w8[4], w8[5]), min(w8[6], w8[7]))));
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 g = fast_noise20(w8[i], noise_c2, noise_c2m);
+                const float2 g = fast_noise20<RWORD>(w8[i], noise_c2, noise_c2m);
                 if constexpr (DUMP) {
                   if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
                 }
@@ -760,7 +864,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         }
         if constexpr (!REPLAY && NOISE32) {
           if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line
-            noise_refill<E, NROUNDS>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
+            noise_refill<E, NROUNDS, RWORD>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
                                      s * (unsigned long long)(N + P) + noise_off + E * t);
         }
         if constexpr (!REPLAY) {
@@ -805,6 +909,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             }
           }
         }
+        if constexpr (FLV) {   // the transform body below starts at the second stage (see the mapper)
+#pragma unroll
+          for (int n = 0; n < E / 2; ++n) {
+            const float2 a = v[n], c = v[n + E / 2];
+            v[n] = cadd(a, c);
+            v[n + E / 2] = csub(a, c);
+          }
+        }
         tsync();
         section_sync<SYNC, BLOCK>();
       }
@@ -822,24 +934,59 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         }
       }
       {
-      fft_dit_inplace<E, -1>(v);
+      fft_dit_inplace<E, -1, FLV ? 1 : 0>(v);
 #pragma unroll
       for (int r = 0; r < E; r += 2) {
         const float2 a = v[fft_out_index<E>(r)], b = v[fft_out_index<E>(r + 1)];
         *reinterpret_cast<float4*>(row + r) = make_float4(a.x, a.y, b.x, b.y);
       }
+      // TWR > 0: the pass-2 twiddles travel through a ring of TWR 128-bit buffers that is filled BEFORE the column loads
+      // (the table is read-only), so that no twiddle load waits behind the 32 column loads in the shared-memory queue and
+      // every later one is requested TWR pairs of legs ahead of its use
+      [[maybe_unused]] float4 ring[TWR > 0 ? TWR : 1];
+      if constexpr (TWR > 0) {
+#pragma unroll
+        for (int b = 0; b < TWR && b < E / 2; ++b) ring[b] = lds128<TWV>(s_tw + tcol * RS + 2 * b);
+      }
       tsync();
 #pragma unroll
-      for (int m = 0; m < E; ++m) u[m] = col[W * RS * m];
+      for (int m = 0; m < E; ++m) u[m] = TWV ? lds64v(col + W * RS * m) : col[W * RS * m];
       tsync();
       section_sync<SYNC, BLOCK>();
+      if constexpr (FTW) {
+        // table row of this lane: {W^(k n), W^(k (n + E/2))} for n < E/2 (k = tcol); the twiddles ride in the first butterflies
 #pragma unroll
-      for (int c = 0; c < E - 1; c += 2) {   // twiddles of legs c + 1 and c + 2 in one 128-bit load (row stride RS: conflict-free)
-        const float4 w = *reinterpret_cast<const float4*>(s_tw + tcol * RS + c);
+        for (int n = 0; n < E / 2; ++n) {
+          float4 w;
+          if constexpr (TWR > 0) {
+            w = ring[n % TWR];
+          } else {
+            w = *reinterpret_cast<const float4*>(s_tw + tcol * RS + 2 * n);
+          }
+          const float2 a = n == 0 ? u[0] : cmul(u[n], make_float2(w.x, w.y)), c = u[n + E / 2];
+          const float2 lo = make_float2(fmaf(-w.w, c.y, fmaf(w.z, c.x, a.x)), fmaf(w.w, c.x, fmaf(w.z, c.y, a.y)));
+          u[n] = lo;
+          u[n + E / 2] = make_float2(fmaf(2.0f, a.x, -lo.x), fmaf(2.0f, a.y, -lo.y));
+          if constexpr (TWR > 0) {
+            if (n + TWR < E / 2) ring[n % TWR] = lds128<TWV>(s_tw + tcol * RS + 2 * (n + TWR));
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < (FTW ? 0 : E - 1); c += 2) {   // twiddles of legs c + 1 and c + 2 in one 128-bit load (row stride RS: conflict-free)
+        float4 w;
+        if constexpr (TWR > 0) {
+          w = ring[(c / 2) % TWR];
+        } else {
+          w = *reinterpret_cast<const float4*>(s_tw + tcol * RS + c);
+        }
         u[c + 1] = cmul(u[c + 1], make_float2(w.x, w.y));
         if (c + 2 < E) u[c + 2] = cmul(u[c + 2], make_float2(w.z, w.w));
+        if constexpr (TWR > 0) {
+          if (c / 2 + TWR < E / 2) ring[(c / 2) % TWR] = lds128<TWV>(s_tw + tcol * RS + c + 2 * TWR);
+        }
       }
-      fft_dit_inplace<E, -1>(u);
+      fft_dit_inplace<E, -1, FTW ? 1 : 0>(u);
       if constexpr (W > 1) {
         // pass-2 output r of butterfly j = t lands at linear index E*E*(t/E) + E*r + (t%E); reload the strided
         // set; radix-W butterflies j = t + T q over the legs u[q + r Q], twiddles W_N^(j r), results in place
@@ -955,8 +1102,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
           const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), top, magic);
           // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
-          rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
-          rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
+          if constexpr (PACKED) {
+            rxc[m >> 2] += (__float_as_uint(tc) << (8 * (m & 3))) + (__float_as_uint(tr) << (8 * (m & 3) + 4));
+          } else {
+            rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
+            rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
+          }
         }
         unsigned be = 0, se = 0;
 #pragma unroll
@@ -982,8 +1133,43 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
             }
             continue;
           }
+          if constexpr (PACKED) {
+            // (0x4B000000 << 8i) + (0x4B000000 << (8i + 4)) mod 2^32 summed over the 4 bytes: only i = 0 survives
+            constexpr unsigned KP = 0x4B000000u + (0x4B000000u << 4);
+            const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
+            const unsigned rx = rxc[j] - KP;
+            const unsigned d = (rx ^ txp[PACKED ? j : 0]) & ((fm >> 1) | (fm << 3));
+            // inverse Gray code inside every nibble: prefix XOR that does not cross nibbles
+            unsigned g = d ^ ((d >> 1) & 0x77777777u);
+            g ^= (g >> 2) & 0x33333333u;
+            be += __popc(g);
+            // bit 7 of every non-zero byte
+            se += __popc((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u);
+            if constexpr (DUMP) {
+              if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int m = 4 * j + i, k = t + T * m;
+                  const unsigned tb = (txp[PACKED ? j : 0] >> (8 * i)) & 0xffu, rb = ((rx & ((fm >> 1) | (fm << 3))) >> (8 * i)) & 0xffu;
+                  auto ig = [](unsigned x) { x ^= x >> 1; x ^= x >> 2; return x & 15u; };
+                  const int hb = ADAPT ? __popc((fmask[ADAPT ? j : 0] >> (8 * i)) & 0xffu) : p.half_bits;
+                  if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((ig(tb >> 4) << hb) | ig(tb & 15u));
+                  if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rb >> 4) << hb) | ig(rb & 15u));
+                }
+              }
+            }
+            continue;
+          }
           const unsigned dc = ((rxc[j] - K) ^ txc[j]) & 0x1E1E1E1Eu;
           const unsigned dr = ((rxr[j] - K) ^ txr[j]) & 0x1E1E1E1Eu;
+          if constexpr (!DUMP && (OPT & kOptJointGray) != 0) {
+            const unsigned d = (dc >> 1) + (dr << 3);                 // column field in the low nibble, row field in the high one
+            unsigned g = d ^ ((d >> 1) & 0x77777777u);               // inverse Gray code inside every nibble
+            g ^= (g >> 2) & 0x33333333u;
+            be += __popc(g);
+            se += __popc((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u);   // bit 7 of every non-zero byte
+            continue;
+          }
           be += __popc(inv_gray_fields(dc) & 0x1E1E1E1Eu) + __popc(inv_gray_fields(dr) & 0x1E1E1E1Eu);
           // a byte of dc | dr is at most 0x1E: adding 0x7F sets its bit 7 exactly when it is non-zero, without carries
           se += __popc(((dc | dr) + 0x7F7F7F7Fu) & 0x80808080u);

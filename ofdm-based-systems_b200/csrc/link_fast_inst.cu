@@ -47,7 +47,8 @@ template <int E, int T, bool DUMP, bool REPLAY, bool ADAPT = false, bool SC = fa
 static int launch_fast_kernel(const ofdm_link* L, const FastParams& p0, cudaStream_t stream) {
   constexpr int BLOCK = 512;
   using G = FastGeometry<E, T, BLOCK>;
-  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT, false, SC, ISI, PSK, 10, 2, TAPS, OPT>;
+  static_assert((OPT & kOptCommon) == kOptCommon, "the link's tables are laid out for the common formulation");
+  auto kern = ofdm_link_fast_kernel<E, T, DUMP, true, REPLAY, BLOCK, SYNC, ADAPT, false, SC, ISI, PSK, kFastRounds, 2, TAPS, OPT>;
   int occ = 1;
   const int rc = blocks_per_sm(kern, G::BLOCK, G::SMEM_BYTES, &occ);
   if (rc != OFDM_OK) return rc;
@@ -101,7 +102,7 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   // the dump-capable kernel evaluates the FIR in the same form as the counters-only kernel of the link (plain complex
   // product for one tap, Gauss form otherwise), so that the two return identical counters
   if (dump)
-    return L->d.n_taps <= 1 ? launch_fast_kernel<E, T, true, false, false, false, false, false, 1, 0, kOptNoise32>(L, p, stream)
+    return L->d.n_taps <= 1 ? launch_fast_kernel<E, T, true, false, false, false, false, false, 1, 0, kOptOneTap>(L, p, stream)
                             : launch_fast_kernel<E, T, true, false>(L, p, stream);
   // The warps of a block run free (SYNC = 0).  Round 1 aligned the warps that share a scheduler at the section
   // boundaries (named barrier per scheduler, SYNC = 2): they then share instruction fetches (stall_no_instruction 0.16
@@ -109,27 +110,13 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   // instruction stream (two Philox calls per 8 noise samples, Gauss-form FIR) free-running warps are faster on every
   // one-warp team shape: -3 % time at N = 1024, -10 % at N = 256, -14 % at N = 64 (profiles/r2_fast_kernel_history.md).
   constexpr int S = 0;
-#ifdef OFDM_FAST_EXPERIMENTS
-  // OFDM_B200_FAST_OPT=<bits> selects the noise / FIR formulation of the headline kernel (tools/time_fused.py sweeps)
-  static const int opt = [] { const char* v = std::getenv("OFDM_B200_FAST_OPT"); return v ? std::atoi(v) : kOptDefault; }();
-  static const int sync = [] { const char* v = std::getenv("OFDM_B200_FAST_SYNC"); return v ? std::atoi(v) : S; }();
-  if (L->d.n_taps > 4 || std::getenv("OFDM_B200_FAST_TAPS8")) {
-    if (sync != S) return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, 2 - S>(L, p, stream);
-    switch (opt) {
-      case 0: return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, 0>(L, p, stream);
-      case 1: return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, 1>(L, p, stream);
-      case 2: return launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, 2>(L, p, stream);
-      default: break;
-    }
-  }
-#endif
   // ZF / no equaliser: sigma2 = 0, so the per-symbol noise estimate of the MMSE form is dropped; one tap: the plain complex
   // product (4 FFMA) beats the Gauss form (3 FFMA + 3 FADD)
   constexpr int kZf = kOptDefault | kOptNoEstimate;
   const bool mmse = L->d.equalizer == OFDM_EQ_MMSE;
   if (L->d.n_taps <= 1)
-    return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptNoise32>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptNoise32 | kOptNoEstimate>(L, p, stream);
+    return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptOneTap>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptOneTap | kOptNoEstimate>(L, p, stream);
   if (L->d.n_taps <= 4)
     return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 4>(L, p, stream)
                 : launch_fast_kernel<E, T, false, false, false, false, false, false, 4, S, kZf>(L, p, stream);

@@ -22,13 +22,15 @@ using namespace ofdm;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 static double g_fsym = 197084.0;
-static std::vector<float2> twiddles(int E) {
+static std::vector<float2> twiddles(int E, bool fused) {
   const int RS = E + 2;
   std::vector<float2> tw(size_t(E) * RS, make_float2(0.f, 0.f));
   for (int k = 0; k < E; ++k)
-    for (int r = 1; r < E; ++r) {
+    for (int r = fused ? 0 : 1; r < E; ++r) {
       const double ang = -2.0 * M_PI * double(k * r) / double(E * E);
-      tw[size_t(k) * RS + r - 1] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      // kOptFusedTwiddle: pairs {W^(k n), W^(k (n + E/2))}
+      const size_t at = fused ? size_t(k) * RS + 2 * (r % (E / 2)) + r / (E / 2) : size_t(k) * RS + r - 1;
+      tw[at] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
   return tw;
 }
@@ -90,14 +92,16 @@ int main(int argc, char** argv) {
     const std::complex<double> A = H * c;      // so that Re(Y conj A) / |A|^2 * ... = level / c
     eq[k] = make_float4((float)A.real(), (float)A.imag(), (float)std::norm(A), (float)(s - 1.0));
   }
-  auto tw = twiddles(E);
+  auto tw = twiddles(E, false), twf = twiddles(E, true);
   { int lg = 0; while ((1 << lg) < N) ++lg; g_fsym = 10.0 * N * lg + 8.0 * L * (N + P) + 4.0 * (N + P) + N * 24.0; }
   static_assert(HE == HT, "harness: two-pass shapes only (no pass-3 twiddles)");
-  float4* d_eq; float2* d_tw; unsigned long long* d_cnt;
+  float4* d_eq; float2* d_tw; float2* d_twf; unsigned long long* d_cnt;
   CK(cudaMalloc(&d_eq, N * sizeof(float4))); CK(cudaMalloc(&d_tw, tw.size() * sizeof(float2)));
   CK(cudaMalloc(&d_cnt, 10 * 8 * kMaxSweepPoints));
   CK(cudaMemcpy(d_eq, eq.data(), N * sizeof(float4), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_twf, twf.size() * sizeof(float2)));
+  CK(cudaMemcpy(d_twf, twf.data(), twf.size() * sizeof(float2), cudaMemcpyHostToDevice));
   p.eq_tab = d_eq; p.tw = d_tw;
   p.slice_top = float(s - 1.0); p.tx_scale2 = 1.f; p.z_unscale = 1.f; p.prefix_len = P; p.zero_prefix = 0; p.equalizer = 2;
   p.half_bits = 3; p.field_mask = 0x0E0E0E0Eu; p.seed = 1; p.point = 0; p.n_points = 1;
@@ -106,9 +110,11 @@ int main(int argc, char** argv) {
   p.sym_begin = 0; p.sym_count = nsym * (1024 / N); p.counters = d_cnt; p.y_scale = 1.f / 32.f;
   const char* only = getenv("ONLY");
 #define VARIANT(name, BLOCK, SYNC, A, F, S, I, K, NR, FU, TAPS, OPT, ...)                                     \
-  if (!only || strstr(name, only))                                                                      \
+  if (!only || strstr(name, only)) {                                                                    \
+    p.tw = ((OPT) & kOptFusedTwiddle) ? d_twf : d_tw;                                                   \
     run(name, ofdm_link_fast_kernel<E, T, false, true, false, BLOCK, SYNC, A, F, S, I, K, NR, FU, TAPS, OPT, ##__VA_ARGS__>, BLOCK, \
-        FastGeometry<E, T, BLOCK>::SMEM_BYTES, p, d_cnt, reps, points);
+        FastGeometry<E, T, BLOCK>::SMEM_BYTES, p, d_cnt, reps, points);                                 \
+  }
 #ifdef WITH_STREAM_EXPERIMENT
 #define VARIANT2(name, BLOCK, TAPS, TRIG)                                                                \
   if (!only || strstr(name, only))                                                                      \
