@@ -282,6 +282,7 @@ int frames_run_impl(const ofdm_frames_desc* d, const double* taps, int64_t n_fra
 
   FastParams fp;
   std::memset(&fp, 0, sizeof(fp));
+  fp.k4b = 0x4B000000u;
   fp.eq_tab = tp.eq;
   fp.tw = d_tw;
   fp.field_masks = tp.masks;

@@ -282,9 +282,6 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 //   4  no per-symbol noise estimate: ZF / no equaliser, where sigma2 = 0 (the MMSE form then needs neither the power sum
 //      over the spectrum nor its shuffles; -3 instructions per subcarrier)
 //   16..240  depth of the twiddle ring of the transform's exchange (bits 4..7; 0 = load each pair at its use)
-//   512  transmitted labels kept as ONE packed word per 4 subcarriers (column index in the low nibble of a byte, row
-//        index in the high nibble) instead of one word per axis: 8 fewer live registers at N = 1024 and half the words
-//        for the error count
 //   1024 pass-2 twiddles fused into the first butterflies of the second codelet: (a, c) <- (w_a a + w_c c, w_a a - w_c c)
 //        costs 10 instructions instead of 12 (table layout: FastParams::tw)
 //   2048 level offset -(s-1) folded into the first butterflies of the transmitter's first codelet: the difference of two
@@ -296,7 +293,7 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 //         y_re = k1 - sum (h_re + h_im) x_im, y_im = k1 + sum (h_im - h_re) x_re
 //   65536 error count on ONE word per 4 subcarriers: the column and row difference fields side by side in a byte
 //         ((dc >> 1) | (dr << 3)), inverse Gray code with nibble-isolating masks
-constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptNoEstimate = 4, kOptPackedLabels = 512, kOptFusedTwiddle = 1024,
+constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptNoEstimate = 4, kOptFusedTwiddle = 1024,
               kOptFusedLevels = 2048, kOptRadiusWord = 4096, kOptIntMax = 8192, kOptDataRounds = 16384, kOptFirChain = 32768, kOptJointGray = 65536;
 constexpr int kOptTwRing4 = (4 << 4) | 256;   // twiddle ring of 4 buffers, volatile loads
 // what every product instantiation uses (the twiddle table of a link is laid out for kOptFusedTwiddle), the one-tap and the
@@ -324,7 +321,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || (!ISI && !FRAMES)), "tap count");
   constexpr bool NOISE32 = (OPT & kOptNoise32) != 0, GAUSS = (OPT & kOptGaussFir) != 0;
   constexpr int TWR = (OPT >> 4) & 15;        // depth of the twiddle ring of the exchange (0: load at use)
-  constexpr bool PACKED = (OPT & kOptPackedLabels) != 0 && !PSK;   // see kOptPackedLabels
   constexpr bool FTW = (OPT & kOptFusedTwiddle) != 0;                             // see kOptFusedTwiddle
   constexpr bool FLV = (OPT & kOptFusedLevels) != 0 && !ADAPT && !PSK && !SC;     // see kOptFusedLevels
   constexpr bool RWORD = (OPT & kOptRadiusWord) != 0, IMAX = (OPT & kOptIntMax) != 0;
@@ -536,7 +532,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
     const uint32_t gs_lo = (uint32_t)gs, gs_hi = (uint32_t)(gs >> 32);
 
     unsigned txc[WORDS], txr[WORDS];  // transmitted level indices, 2*index at bits 1..4 of each byte
-    [[maybe_unused]] unsigned txp[PACKED ? WORDS : 1];   // PACKED: column | row << 4 per byte; txc / txr die after the mapper
     float2 v[E];
 
     // ---- transmitter epilogue: PAPR statistics of the time samples x[t + T m] = sample(m) and their publication
@@ -633,7 +628,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
               const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
               txc[j] = (txc[j] ^ (txc[j] >> 1)) & fm;
               txr[j] = (txr[j] ^ (txr[j] >> 1)) & fm;
-              if constexpr (PACKED) txp[j] = (txc[j] >> 1) | (txr[j] << 3);
             }
           }
           tsync();
@@ -652,7 +646,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
                 } else {
                   txc[4 * c + j] = (ww[j] << 1) & fm;   // bits 0..3 of each byte -> column index
                   txr[4 * c + j] = (ww[j] >> 3) & fm;   // bits 4..7 of each byte -> row index
-                  if constexpr (PACKED) txp[4 * c + j] = ww[j] & ((fm >> 1) | (fm << 3));
                 }
               }
             }
@@ -826,11 +819,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
               wmin = min(min(wmin, min(w8[0], w8[1])), min(min(w8[2], w8[3]), min(min(w8[4], w8[5]), min(w8[6], w8[7]))));
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 g = fast_noise20<RWORD>(w8[i], noise_c2, noise_c2m);
+                // explicit fused add: whether rad * d + y contracts must not depend on the instantiation (the dump-capable
+                // kernel also needs the product on its own), the counters of the two are compared for equality
+                const float rad = noise20_radius<RWORD>(w8[i], noise_c2, noise_c2m);
+                const float2 d = noise20_dir(w8[i]);
                 if constexpr (DUMP) {
-                  if (active && p.dump_noise) p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = g;
+                  if (active && p.dump_noise)
+                    p.dump_noise[s * (unsigned long long)(N + P) + noise_off + E * t + 8 * c + i] = make_float2(__fmul_rn(rad, d.x), __fmul_rn(rad, d.y));
                 }
-                y[i] = cadd(y[i], g);
+                y[i] = make_float2(__fmaf_rn(rad, d.x, y[i].x), __fmaf_rn(rad, d.y, y[i].y));
               }
             } else if constexpr (!REPLAY) {
               // 8 complex samples from 3 Philox calls: 8 x 32-bit radius words + 8 x 16-bit angle fields
@@ -1102,12 +1099,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           const float tc = fmaf(__saturatef(fmaf(a, inv, 0.5f)), top, magic);
           const float tr = fmaf(__saturatef(fmaf(b, inv, 0.5f)), top, magic);
           // accumulate 2*index into byte (m & 3) of the packed word; the 0x4B000000 parts cancel below
-          if constexpr (PACKED) {
-            rxc[m >> 2] += (__float_as_uint(tc) << (8 * (m & 3))) + (__float_as_uint(tr) << (8 * (m & 3) + 4));
-          } else {
-            rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
-            rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
-          }
+          rxc[m >> 2] += __float_as_uint(tc) << (8 * (m & 3) + 1);
+          rxr[m >> 2] += __float_as_uint(tr) << (8 * (m & 3) + 1);
         }
         unsigned be = 0, se = 0;
 #pragma unroll
@@ -1128,33 +1121,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
                   const int k = t + T * (4 * j + i);
                   if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((txc[j] >> (8 * i)) & 0xffu);
                   if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((rxc[j] >> (8 * i)) & 0xffu);
-                }
-              }
-            }
-            continue;
-          }
-          if constexpr (PACKED) {
-            // (0x4B000000 << 8i) + (0x4B000000 << (8i + 4)) mod 2^32 summed over the 4 bytes: only i = 0 survives
-            constexpr unsigned KP = 0x4B000000u + (0x4B000000u << 4);
-            const unsigned fm = ADAPT ? fmask[ADAPT ? j : 0] : p.field_mask;
-            const unsigned rx = rxc[j] - KP;
-            const unsigned d = (rx ^ txp[PACKED ? j : 0]) & ((fm >> 1) | (fm << 3));
-            // inverse Gray code inside every nibble: prefix XOR that does not cross nibbles
-            unsigned g = d ^ ((d >> 1) & 0x77777777u);
-            g ^= (g >> 2) & 0x33333333u;
-            be += __popc(g);
-            // bit 7 of every non-zero byte
-            se += __popc((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u);
-            if constexpr (DUMP) {
-              if (active) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int m = 4 * j + i, k = t + T * m;
-                  const unsigned tb = (txp[PACKED ? j : 0] >> (8 * i)) & 0xffu, rb = ((rx & ((fm >> 1) | (fm << 3))) >> (8 * i)) & 0xffu;
-                  auto ig = [](unsigned x) { x ^= x >> 1; x ^= x >> 2; return x & 15u; };
-                  const int hb = ADAPT ? __popc((fmask[ADAPT ? j : 0] >> (8 * i)) & 0xffu) : p.half_bits;
-                  if (p.dump_tx) p.dump_tx[s * N + k] = (unsigned short)((ig(tb >> 4) << hb) | ig(tb & 15u));
-                  if (p.dump_rx) p.dump_rx[s * N + k] = (unsigned short)((ig(rb >> 4) << hb) | ig(rb & 15u));
                 }
               }
             }

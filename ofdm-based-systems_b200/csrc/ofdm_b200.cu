@@ -220,6 +220,7 @@ void fill_fast(const ofdm_link* L, FastParams& f, double snr_db, const ofdm_link
   while ((1 << (2 * half_bits)) < M) ++half_bits;
   const int side = 1 << half_bits;
   std::memset(&f, 0, sizeof(f));
+  f.k4b = 0x4B000000u;
   std::memcpy(f.taps, L->taps_fast, sizeof(f.taps));
   for (int l = 0; l < kFastTaps; ++l)   // Gauss form of the complex product (link_fast.cuh, FIR stage)
     f.taps3[l] = make_float4(L->taps_fast[l].x, L->taps_fast[l].y - L->taps_fast[l].x, L->taps_fast[l].x + L->taps_fast[l].y, 0.f);
