@@ -93,7 +93,8 @@ uint64_t ofdm_link_table_bytes(const ofdm_link* link);
 
 /* Fused Monte-Carlo mode: replaces simulation/models.py:454-606 for OFDM symbols
  * [first_symbol, first_symbol + n_symbols) of SNR point `point`; bits and AWGN come from
- * Philox4x32-10 keyed by `seed` with counter (symbol, stream, point), so any sharding of the symbol
+ * Philox4x32 (7 rounds on the fast kernel, 10 on the general one) keyed by `seed` with counter
+ * (symbol, stream, point), so any sharding of the symbol
  * range over GPUs produces the same union.  noise_sigma is the per-component standard deviation
  * sqrt(mean|stream|^2 / snr_lin / 2) (noise/models.py:14-20), computed by the caller.
  * Synchronous: returns when `out` is filled.  dump pointers, if given, are HOST memory. */

@@ -209,19 +209,18 @@ __device__ __forceinline__ float2 fast_noise(uint32_t wr, uint32_t wa, uint32_t 
 //   angle = 2 pi (a + 0.5) / 4096 - pi via the mantissa of 2^23 + a: 4096 equally spaced rays are invisible after any
 //   projection (the radius is continuous) and noise is rotation invariant.
 constexpr uint32_t kRefillBelow = 4096u;   // w < 4096  <=>  radius field == 0
-template <bool WORD = false>
 __device__ __forceinline__ float noise20_radius(uint32_t w, float c2, float c2m) {
-  // WORD: u = w 2^-32 straight from the word (the angle field only moves u inside its 2^-20 cell)
-  return fast_sqrt(fmaf(c2, fast_lg2((float)(WORD ? w : (w | 0xFFFu))), c2m));
+  // the OR is not optional: u straight from the word saves it, but w = 0 (once per 2^32 samples) then gives an infinite
+  // radius that poisons its whole OFDM symbol - bench.py's 1e12-bit record caught 29 such symbols
+  return fast_sqrt(fmaf(c2, fast_lg2((float)(w | 0xFFFu)), c2m));
 }
 __device__ __forceinline__ float2 noise20_dir(uint32_t w) {
   const float f = __uint_as_float((w & 0xFFFu) | 0x4B000000u);                                   // 2^23 + a
   const float ang = fmaf(f, 1.5339807878856412e-03f, -12871.104692850697f);                      // (2 pi / 4096)(a + 0.5) - pi (offset for the ROUNDED slope)
   return make_float2(__cosf(ang), __sinf(ang));
 }
-template <bool WORD = false>
 __device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m) {
-  const float rad = noise20_radius<WORD>(w, c2, c2m);
+  const float rad = noise20_radius(w, c2, c2m);
   const float2 d = noise20_dir(w);
   return make_float2(rad * d.x, rad * d.y);
 }
@@ -229,7 +228,7 @@ __device__ __forceinline__ float2 fast_noise20(uint32_t w, float c2, float c2m) 
 // Rare path of the 32-bit-per-sample noise: at least one of this lane's E radius fields was 0.  Regenerates the lane's
 // words, and for every sample with a zero field draws 32 fresh bits r: u = (r + 0.5) 2^-52, same direction; the FIR
 // output in `row` already holds the coarse sample, so the difference is added.
-template <int E, int NROUNDS, bool WORD = false>
+template <int E, int NROUNDS>
 __device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, uint32_t gs_hi, uint32_t point, PhiloxKey key,
                                           float c2, float c2m, float2* dump_noise, unsigned long long dump_base) {
 #pragma unroll 1
@@ -246,7 +245,7 @@ __device__ __noinline__ void noise_refill(float2* row, int t, uint32_t gs_lo, ui
         const uint4 r = philox4x32<NROUNDS>(make_uint4(gs_lo, gs_hi, (1u << 28) | (1u << 20) | uint32_t(E * t + i), point), key);
         const float u = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (r + 0.5) 2^-32
         const float rad_new = fast_sqrt(c2 * (fast_lg2(u) - 20.0f));
-        const float rad_old = noise20_radius<WORD>(w, c2, c2m);
+        const float rad_old = noise20_radius(w, c2, c2m);
         const float2 d = noise20_dir(w);
         const float2 o = row[i];
         row[i] = make_float2(fmaf(rad_new - rad_old, d.x, o.x), fmaf(rad_new - rad_old, d.y, o.y));
@@ -286,7 +285,6 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 //        costs 10 instructions instead of 12 (table layout: FastParams::tw)
 //   2048 level offset -(s-1) folded into the first butterflies of the transmitter's first codelet: the difference of two
 //        2^23-based label floats needs no offset, their sum one (6 FADD per butterfly instead of 8)
-//   4096 noise radius from the whole 32-bit word, lg2(float(w)), without masking the angle field out first
 //   8192 PAPR maximum with 3-input integer maxima on the bit patterns (non-negative floats order like integers)
 //   16384 the data-bit Philox calls use NROUNDS like the noise calls
 //   32768 Gauss-form FIR without the two final additions: the k3 and k2 sums continue the k1 chain,
@@ -294,12 +292,12 @@ __device__ __forceinline__ unsigned inv_gray_fields(unsigned x) {
 //   65536 error count on ONE word per 4 subcarriers: the column and row difference fields side by side in a byte
 //         ((dc >> 1) | (dr << 3)), inverse Gray code with nibble-isolating masks
 constexpr int kOptNoise32 = 1, kOptGaussFir = 2, kOptNoEstimate = 4, kOptFusedTwiddle = 1024,
-              kOptFusedLevels = 2048, kOptRadiusWord = 4096, kOptIntMax = 8192, kOptDataRounds = 16384, kOptFirChain = 32768, kOptJointGray = 65536;
+              kOptFusedLevels = 2048, kOptIntMax = 8192, kOptDataRounds = 16384, kOptFirChain = 32768, kOptJointGray = 65536;
 constexpr int kOptTwRing4 = (4 << 4) | 256;   // twiddle ring of 4 buffers, volatile loads
 // what every product instantiation uses (the twiddle table of a link is laid out for kOptFusedTwiddle), the one-tap and the
 // multi-tap formulation of the channel; profiles/r2_fast_kernel_history.md section 7 has the measurements, the A/B harness
 // (tools/microbench/fast_variants.cu) still builds the formulations without them
-constexpr int kOptCommon = kOptFusedTwiddle | kOptFusedLevels | kOptRadiusWord | kOptIntMax | kOptDataRounds | kOptFirChain |
+constexpr int kOptCommon = kOptFusedTwiddle | kOptFusedLevels | kOptIntMax | kOptDataRounds | kOptFirChain |
                            kOptJointGray | kOptTwRing4;
 constexpr int kOptOneTap = kOptNoise32 | kOptCommon, kOptDefault = kOptNoise32 | kOptGaussFir | kOptCommon;
 
@@ -318,12 +316,12 @@ template <int E, int T, bool DUMP, bool PAPR, bool REPLAY = false, int BLOCK = 5
 __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __grid_constant__ FastParams p) {
   // MINB: blocks per SM the register allocation must allow (2 for the narrow codelets: 64 registers, 32 warps per SM)
   // TAPS: channel taps the FIR evaluates (the host zero-pads the tap table, so a shorter loop only drops exact zeros)
-  static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || (!ISI && !FRAMES)), "tap count");
+  static_assert(TAPS >= 1 && TAPS <= kFastTaps && (TAPS == kFastTaps || !FRAMES), "tap count");
   constexpr bool NOISE32 = (OPT & kOptNoise32) != 0, GAUSS = (OPT & kOptGaussFir) != 0;
   constexpr int TWR = (OPT >> 4) & 15;        // depth of the twiddle ring of the exchange (0: load at use)
   constexpr bool FTW = (OPT & kOptFusedTwiddle) != 0;                             // see kOptFusedTwiddle
   constexpr bool FLV = (OPT & kOptFusedLevels) != 0 && !ADAPT && !PSK && !SC;     // see kOptFusedLevels
-  constexpr bool RWORD = (OPT & kOptRadiusWord) != 0, IMAX = (OPT & kOptIntMax) != 0;
+  constexpr bool IMAX = (OPT & kOptIntMax) != 0;
   constexpr int DROUNDS = (OPT & kOptDataRounds) ? NROUNDS : 10;
   constexpr bool TWV = (OPT & 256) != 0;       // ring and column loads as volatile accesses (keeps their order in SASS)
   // PSK: M-ary phase-shift keying, one order on every subcarrier; labels through a shared-memory point table at the
@@ -821,7 +819,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
               for (int i = 0; i < 8; ++i) {
                 // explicit fused add: whether rad * d + y contracts must not depend on the instantiation (the dump-capable
                 // kernel also needs the product on its own), the counters of the two are compared for equality
-                const float rad = noise20_radius<RWORD>(w8[i], noise_c2, noise_c2m);
+                const float rad = noise20_radius(w8[i], noise_c2, noise_c2m);
                 const float2 d = noise20_dir(w8[i]);
                 if constexpr (DUMP) {
                   if (active && p.dump_noise)
@@ -861,7 +859,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         }
         if constexpr (!REPLAY && NOISE32) {
           if (wmin < kRefillBelow)   // probability 2^-20 per sample: out of line
-            noise_refill<E, NROUNDS, RWORD>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
+            noise_refill<E, NROUNDS>(row, t, gs_lo, gs_hi, point, key, noise_c2, noise_c2m, (DUMP && active) ? p.dump_noise : nullptr,
                                      s * (unsigned long long)(N + P) + noise_off + E * t);
         }
         if constexpr (!REPLAY) {
@@ -998,19 +996,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const float2 w1 = s_tw3[t + T * q];
+          // FMA-fused butterflies: a + w c costs 4 FFMA and a - w c = 2 a - (a + w c) two more
+          auto fused = [](float2& a, float2& c, float2 w) {
+            const float2 lo = make_float2(fmaf(-w.y, c.y, fmaf(w.x, c.x, a.x)), fmaf(w.y, c.x, fmaf(w.x, c.y, a.y)));
+            c = make_float2(fmaf(2.0f, a.x, -lo.x), fmaf(2.0f, a.y, -lo.y));
+            a = lo;
+          };
           if constexpr (W == 2) {
-            const float2 a = u[q], b = cmul(u[q + Q], w1);
-            u[q] = cadd(a, b);
-            u[q + Q] = csub(a, b);
+            fused(u[q], u[q + Q], w1);
           } else {
-            const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-            const float2 a0 = u[q], a1 = cmul(u[q + Q], w1), a2 = cmul(u[q + 2 * Q], w2), a3 = cmul(u[q + 3 * Q], w3);
-            const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
-            const float2 jd = make_float2(d13.y, -d13.x);   // -j (a1 - a3)
-            u[q] = cadd(s02, s13);
-            u[q + Q] = cadd(d02, jd);
-            u[q + 2 * Q] = csub(s02, s13);
-            u[q + 3 * Q] = csub(d02, jd);
+            // radix 4 as two radix-2 steps: with w3 = w1 w2, w1 a1 +- w3 a3 = w1 (a1 +- w2 a3), so the legs need w2 first and
+            // w1 (times 1 or -j) in the second step: X0,2 = (a0 + w2 a2) +- w1 (a1 + w2 a3), X1,3 = (a0 - w2 a2) -+ j w1 (a1 - w2 a3)
+            const float2 w2 = cmul(w1, w1);
+            fused(u[q], u[q + 2 * Q], w2);
+            fused(u[q + Q], u[q + 3 * Q], w2);
+            fused(u[q], u[q + Q], w1);                                      // X0 -> u[q], X2 -> u[q + Q]
+            fused(u[q + 2 * Q], u[q + 3 * Q], make_float2(w1.y, -w1.x));    // X1 -> u[q + 2Q], X3 -> u[q + 3Q]
+            const float2 x2 = u[q + Q];
+            u[q + Q] = u[q + 2 * Q];
+            u[q + 2 * Q] = x2;
           }
         }
       }

@@ -89,8 +89,10 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
 #define OFDM_FAST_VARIANT(ADAPT_, SC_, ISI_, PSK_)                                                                     \
   do {                                                                                                                 \
     if (replay) return launch_fast_kernel<E, T, true, true, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                    \
-    return dump ? launch_fast_kernel<E, T, true, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream)                         \
-                : launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                       \
+    if (dump) return launch_fast_kernel<E, T, true, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                     \
+    /* channels of at most 4 taps (every shipped model but two): the FIR skips the four exact zeros */                 \
+    return L->d.n_taps <= 4 ? launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_, 4>(L, p, stream)         \
+                            : launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);           \
   } while (0)
   if (psk) OFDM_FAST_VARIANT(false, false, false, true);       // M-ary PSK, one order
   if (isi && sc) OFDM_FAST_VARIANT(false, true, true, false);  // SC-OFDM with a prefix shorter than the channel memory

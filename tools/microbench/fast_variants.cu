@@ -117,14 +117,14 @@ int main(int argc, char** argv) {
   }
 #ifdef WITH_STREAM_EXPERIMENT
 #define VARIANT2(name, BLOCK, TAPS, TRIG)                                                                \
-  if (!only || strstr(name, only))                                                                      \
+  if ((p.tw = d_tw, !only) || strstr(name, only))                                                        \
     run(name, ofdm_link_stream_kernel<E, T, BLOCK, false, false, TAPS, TRIG>, BLOCK, StreamGeometry<E, T, BLOCK>::SMEM_BYTES, p, d_cnt, reps, points);
 #else
 #define VARIANT2(name, BLOCK, TAPS, TRIG)
 #endif
 #ifdef WITH_STREAM_EXPERIMENT
 #define VARIANT3(name, MODE)                                                                             \
-  if (!only || strstr(name, only))                                                                      \
+  if ((p.tw = d_tw, !only) || strstr(name, only))                                                        \
     run(name, ofdm_link_stream2_kernel<E, T, 512, MODE, 8>, 512, StreamGeometry<E, T, 512>::SMEM_BYTES + (((MODE) & 10) == 10 ? 32768 : 0), p, d_cnt, reps, points);
 #else
 #define VARIANT3(name, MODE)
