@@ -97,6 +97,18 @@ def test_full_size_counters_are_additive_and_reproducible(n, order, per_launch):
     link.close()
 
 
+def test_no_noise_sample_poisons_an_ofdm_symbol():
+    """1e12 bits of BASELINE config #5 (N = 4096, 256-QAM, MMSE) at an SNR where thermal errors are impossible: every noise
+    word the generator can produce must give a finite sample.  A radius taken straight from the 32-bit word (lg2(0) for w = 0,
+    once per 2^32 samples) turned ~29 OFDM symbols of such a run into NaNs - 16 384 bit errors each (simulation/models.py:597-606
+    counts them like any other)."""
+    link = headline_link(order=256, n=4096)
+    sigma = float(np.sqrt(1 / 10 ** 5.5 / 2))
+    r = link.run_fused(55.0, sigma, 30_518_000, seed=0x0FD3)
+    link.close()
+    assert r.bits >= 10 ** 12 and r.bit_errors == 0 and r.symbol_errors == 0
+
+
 VARIANTS = [
     # name, N, order, scheme, channel, prefix, P, eq, modulator, per-subcarrier orders?
     ("qam", 1024, 64, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", "OFDM", False),
@@ -120,6 +132,9 @@ VARIANTS = [
     ("flat_mmse", 256, 64, "QAM", "flat_fading", "CYCLIC", 4, "MMSE", "OFDM", False),
     ("isi_zp", 256, 64, "QAM", "severe_multipath", "ZERO", 3, "MMSE", "OFDM", False),
     ("isi_zp_sc", 128, 4, "QAM", "Lin-Phoong_P2", "ZERO", 1, "MMSE", "SC-OFDM", False),
+    # the 4-tap instantiations of the loading and the chained-symbol kernels (the dump-capable twin evaluates 8 taps)
+    ("adaptive_4taps", 64, 0, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "OFDM", True),
+    ("isi_4taps", 64, 64, "QAM", "Lin-Phoong_P2", "CYCLIC", 1, "MMSE", "OFDM", False),
 ]
 
 
