@@ -373,6 +373,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   // same circular convolution as a cyclic-prefixed one.  What differs: no prefix power in the PAPR statistics (Pc = 0),
   // the noise of the P folded tail samples adds to the first P samples, and the stream index of sample n is n, not P + n.
   const int Pc = p.zero_prefix ? 0 : P, noise_off = p.zero_prefix ? 0 : P;
+  // Narrow teams (E = 8): a cyclic prefix of the usual length covers more than one row of samples (BASELINE config #1:
+  // N = 64, CP = 16), so the power weights of this lane's samples - 2 for the ones the prefix repeats, n = t + T m >= N - Pc -
+  // live in E registers and the sum is one FFMA per sample, whatever the prefix length
+  constexpr bool PWGT = PAPR && E <= 8;
+  [[maybe_unused]] float pwgt[PWGT ? E : 1];
+  if constexpr (PWGT) {
+#pragma unroll
+    for (int m = 0; m < E; ++m) pwgt[m] = (t + T * m >= N - Pc) ? 2.f : 1.f;
+  }
   const float magic = 8388608.0f;  // 2^23
   // symbols of this pass: s = s_lo + it * s_stride + s_first < s_hi, global index sym_base + s.  One pass over the
   // launch's range, or (FRAMES) one pass per (frame, chunk) unit with the whole block on the same frame.
@@ -544,7 +553,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           if constexpr (PAPR) {
             const float pw = fmaf(x.x, x.x, x.y * x.y);
             // the cyclic prefix repeats the last P samples; for P <= T: n = t + T m >= N - P  <=>  m == E-1, t >= T - P
-            ssum[m & 3] += (m == E - 1 && t >= T - Pc) ? 2.f * pw : pw;
+            if constexpr (PWGT) {
+              ssum[m & 3] = fmaf(pw, pwgt[PWGT ? m : 0], ssum[m & 3]);
+            } else {
+              ssum[m & 3] += (m == E - 1 && t >= T - Pc) ? 2.f * pw : pw;
+            }
             if constexpr (IMAX) {
               if (m & 1) imax[(m >> 1) & 1] = __vimax3_u32(imax[(m >> 1) & 1], __float_as_uint(pw_prev), __float_as_uint(pw));
               pw_prev = pw;
@@ -555,7 +568,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           col[W * RS * m] = x;
         }
         if constexpr (PAPR && IMAX) smax[0] = __uint_as_float(max(imax[0], imax[1]));
-        if (PAPR && Pc > T) {
+        if (PAPR && !PWGT && Pc > T) {
           // long prefix (more than one row of samples): the rows above the last one that it also repeats; rolled
           // loop over this lane's own samples in shared memory (rare shape, keeps the instruction stream small)
           const int pm = (N - Pc) / T, pt = (N - Pc) % T;
