@@ -32,6 +32,7 @@ ap.add_argument("--bits", type=float, default=1e9)
 ap.add_argument("--launches", type=int, default=3)
 ap.add_argument("--time", type=int, default=0)
 ap.add_argument("--points", type=int, default=1)
+ap.add_argument("--adaptive", action="store_true", help="per-subcarrier orders drawn from {0, 4, 16, 64, 256} (loading tables)")
 a = ap.parse_args()
 
 taps = np.load(os.path.join(ROOT, "config", "channel_models", a.taps + ".npy")).astype(np.complex128)
@@ -41,7 +42,11 @@ bps = int(np.log2(a.order))
 nsym = int(-(-a.bits // (a.n * bps)))
 h_eq = np.fft.fft(taps, a.n)
 tn = taps / np.sqrt(np.sum(np.abs(taps) ** 2))
-link = nat.Link(a.n, tn, h_eq, np.full(a.n, a.order), prefix_type=a.prefix_type, prefix_len=prefix, equalizer=a.eq,
+orders = np.random.default_rng(1).choice([0, 4, 16, 64, 256], size=a.n) if a.adaptive else np.full(a.n, a.order)
+if a.adaptive:
+    bps = float(np.mean([int(np.log2(o)) if o > 1 else 0 for o in orders]))
+    nsym = int(-(-a.bits // (a.n * bps)))
+link = nat.Link(a.n, tn, h_eq, orders, prefix_type=a.prefix_type, prefix_len=prefix, equalizer=a.eq,
                 modulator=a.modulator, scheme=a.scheme)
 sigma = float(np.sqrt(1 / 10 ** (a.snr / 10) / 2))
 c_eq = {"MMSE": 14, "ZF": 6, "NONE": 0}[a.eq]
@@ -74,7 +79,7 @@ if a.time:
     else:
         link.read_result()
     dt = (time.perf_counter() - t0) / a.time
-    bits = nsym * a.n * bps * a.points
+    bits = int(nsym * a.n * bps * a.points)
     print(f"TIME N={a.n} M={a.order} L={L} P={prefix} {a.eq} {a.modulator} points={a.points}: {dt * 1e3:.4f} ms/launch "
           f"{bits / dt:.4e} bits/s  F_sym={f_sym}  alg {f_sym * nsym * a.points / dt / 1e12:.2f} TFLOP/s "
           f"({100 * f_sym * nsym * a.points / dt / 1e12 / 72.6:.1f} % of 72.6)")
