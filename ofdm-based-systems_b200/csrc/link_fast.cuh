@@ -12,8 +12,11 @@
 //   * a team of T lanes (one warp for N = 1024) owns an OFDM symbol, E samples per lane in registers;
 //   * ONE forward-FFT body serves both transforms (the IFFT runs as an FFT on re/im-swapped data) and the
 //     FIR + AWGN stage is a rolled loop over 8-sample chunks that works in place in shared memory, so the
-//     per-symbol instruction stream stays small; the warps that share a scheduler walk it in step (named
-//     barrier per scheduler) so that they share instruction-cache lines;
+//     per-symbol instruction stream stays small; the warps of a block run free (SYNC = 0; SYNC = 2, round 1's choice,
+//     keeps the warps that share a scheduler in step so that they share instruction-cache lines);
+//   * the kernel is bound by the issue rate, so the formulation removes instructions wherever the algebra allows: the
+//     inter-pass twiddles and the mapper's level offset ride in first-stage butterflies, the Gauss-form FIR sums are
+//     chained, the error count works on one word per four subcarriers (kOpt* below, profiles/r2_fast_kernel_history.md);
 //   * every scale factor (1/sqrt(2(M-1)/3), both 1/sqrt(N), the slicer's k/2 and 1/(s-1)) is folded on the
 //     host into the FIR taps and the equaliser table; level <-> index conversions use mantissa tricks and
 //     FFMA.SAT (no I2F / F2I / FMNMX);
