@@ -177,6 +177,18 @@ def cpu_baseline_single(budget_s: float = 14.0) -> dict:
     return out
 
 
+def arm_config(world: int, warmup: int) -> dict:
+    """`config` of the JSON line - ONE definition for both arms, so that the driver sees the same object on the reference
+    line (`--impl reference` runs the reference "on your arm's config"); what only the GPU arm does (L2 flush, untimed
+    steps, collective) is said here once and is simply not applicable to the CPU run."""
+    bits_per_step = SYMBOLS_PER_POINT * BITS_PER_OFDM * len(SNR_GRID) * world      # whole job
+    return {"workload": WORKLOAD, "snr_grid_db": SNR_GRID, "symbols_per_point_per_gpu": SYMBOLS_PER_POINT, "bits_per_step": bits_per_step,
+            "untimed_steps": max(warmup, 3) + 30,
+            "untimed_steps_why": "max(W, 3) warm-up steps + 30 (~0.5 s) so that nvidia-smi (100 ms period) samples the clocks under this load",
+            "parallelism": f"symbol-range shards x{world}, ONE NCCL all-reduce per sweep (= per step), issued on the process group's stream behind the step's kernel so that the next step's kernel does not wait for it" if world > 1 else "1 GPU (no collective)",
+            "l2": "144 MiB (151 MB > 126 MB L2) memset between timed steps, inside the timed region; the kernel's inputs are generated in registers (86 KB of tables read per launch)"}
+
+
 def run_reference_arm(args) -> None:
     """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: the unmodified package, copied
     by oracle/build_ref.py; the NumPy port only if that copy is absent) on all host cores, one independent process per
@@ -203,7 +215,7 @@ def run_reference_arm(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bits/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
+            "config": arm_config(args.gpus, args.warmup),   # the GPU arm's config, verbatim: same workload, same grid
             "step_sample": f"{per_step} x {n_ofdm} OFDM symbols on {cores} host processes per step (a bounded sample of the workload)",
             "cpu_baseline": {"value": value, "unit": "bits/s", "cores": cores, "kind": kind,
                              "sample": f"{args.steps} steps x {per_step} chunks x {n_ofdm} OFDM symbols cycling through the SNR grid, {what}"},
@@ -330,10 +342,7 @@ def run_b200_arm(args) -> None:
             "metric": METRIC, "value": value, "unit": "bits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "snr_grid_db": snrs, "symbols_per_point_per_gpu": S, "bits_per_step": bits_per_step,
-                       "untimed_steps": w, "untimed_steps_why": "max(W, 3) warm-up steps + 30 (~0.5 s) so that nvidia-smi (100 ms period) samples the clocks under this load",
-                       "parallelism": f"symbol-range shards x{world}, ONE NCCL all-reduce per sweep (= per step), issued on the process group's stream behind the step's kernel so that the next step's kernel does not wait for it" if world > 1 else "1 GPU (no collective)",
-                       "l2": "144 MiB (151 MB > 126 MB L2) memset between timed steps, inside the timed region; the kernel's inputs are generated in registers (86 KB of tables read per launch)"},
+            "config": arm_config(world, args.warmup),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "bits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": "LinkSweep(cfg).sweep(grid) per step: link built from host taps / orders (tables staged in pinned memory, one H2D copy), ONE kernel launch for the 16 points, all-reduce when N > 1, counters D2H"},
