@@ -225,3 +225,40 @@ def test_noise_tails_follow_the_gaussian(kat):
     # independence of neighbouring samples and of the two components
     assert abs(np.mean(x[:-1] * x[1:])) < 5 / np.sqrt(m)
     assert abs(np.mean(w.real * w.imag)) / sigma ** 2 < 5 / np.sqrt(m / 2)
+
+
+def test_noise_stream_is_white_across_calls_lanes_symbols_and_points(kat):
+    """The fast kernel draws its noise from Philox4x32 with SEVEN rounds.  Beyond the marginal distribution
+    (test above): no correlation between samples of the same Philox call, of neighbouring calls, of neighbouring lanes
+    (32 samples apart), of neighbouring OFDM symbols and of two SNR points, fourth and sixth moments of a Gaussian, squares
+    uncorrelated too (a weak generator shows up in the squares first), noise independent of the data labels."""
+    from ofdm_based_systems._native import Link
+    n, P, n_ofdm, sigma = 1024, 7, 6000, 0.21
+    taps = oc.normalize_taps(kat["chan_severe_multipath"])
+    link = Link(n, taps, np.fft.fft(taps, n), np.full(n, 64), prefix_type="CYCLIC", prefix_len=P)
+    _, d0 = link.run_fused(15.0, sigma, n_ofdm, seed=77, point=0, dump=("noise", "tx_labels"))
+    _, d1 = link.run_fused(15.0, sigma, n_ofdm, seed=77, point=1, dump=("noise",))
+    link.close()
+    w0 = d0["noise"][:, P:].astype(np.complex128) / sigma           # [symbol, sample]: sample i of a symbol is word i % 4 of call i // 4
+    w1 = d1["noise"][:, P:].astype(np.complex128) / sigma
+    m = w0.size
+    tol = 5.0 / np.sqrt(m)
+
+    def corr(a, b):
+        return abs(np.mean(a * np.conj(b)))
+
+    for lag in (1, 2, 3, 4, 5, 8, 32, 33, 64, 512):                  # inside a call, across calls, across lanes
+        assert corr(w0[:, lag:], w0[:, :-lag]) < 1.5 * tol, lag
+        assert abs(np.mean(w0[:, lag:] * w0[:, :-lag])) < 1.5 * tol, lag           # non-circular part
+    assert corr(w0[1:], w0[:-1]) < 1.5 * tol                          # same sample index, neighbouring OFDM symbols
+    assert corr(w0, w1) < 1.5 * tol                                   # same counters, neighbouring SNR points
+    x = np.concatenate([w0.real.ravel(), w0.imag.ravel()])
+    assert abs(np.mean(x ** 4) - 3.0) < 5 * np.sqrt(96.0 / x.size)    # var(x^4) = 96
+    assert abs(np.mean(x ** 6) - 15.0) < 5 * np.sqrt(10170.0 / x.size)
+    p0 = np.abs(w0) ** 2 - 2.0                                         # centred powers: E = 0, var = 4
+    for lag in (1, 4, 32):
+        assert abs(np.mean(p0[:, lag:] * p0[:, :-lag])) < 5 * 4.0 / np.sqrt(m), lag
+    assert abs(np.mean(p0 * (np.abs(w1) ** 2 - 2.0))) < 5 * 4.0 / np.sqrt(m)
+    lab = d0["tx_labels"].astype(np.float64)
+    lab -= lab.mean()
+    assert abs(np.mean(lab * w0.real)) < 5 * lab.std() / np.sqrt(m) and abs(np.mean(lab * p0)) < 5 * 2 * lab.std() / np.sqrt(m)
