@@ -355,7 +355,7 @@ def run_b200_arm(args) -> None:
                          "peak_source": "FFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no FP32 figure); "
                                         "frac_nominal uses 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.45 TFLOP/s",
                          "rng": "bits and noise from Philox4x32-7 (the crush-resistant minimum, DESIGN.md 3.3); the library built with "
-                                "OFDM_FAST_PHILOX_ROUNDS=10 measures frac 0.504 on this step (profiles/r2_fast_kernel_history.md section 7)"},
+                                "OFDM_FAST_PHILOX_ROUNDS=10 measures frac 0.503 with this same command (profiles/r2_bench_line_philox10.json)"},
             "check": {"bit_error_rate_20db": at20["bit_error_rate"], "bits_20db": at20["total_bits"], "papr_db": at20["papr_db"],
                       "strong_bit_errors": int(sum(r["bit_errors"] for r in strong)),
                       "strong_bit_errors_per_point": [int(r["bit_errors"]) for r in strong],
