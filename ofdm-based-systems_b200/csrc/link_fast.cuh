@@ -329,12 +329,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   constexpr bool TWV = (OPT & 256) != 0;       // ring and column loads as volatile accesses (keeps their order in SASS)
   // PSK: M-ary phase-shift keying, one order on every subcarrier; labels through a shared-memory point table at the
   // transmitter, angle rounding at the receiver (the equaliser's positive real denominator does not move the angle)
-  static_assert(!PSK || (!ADAPT && !FRAMES && !SC && !ISI), "PSK: one order, single link, OFDM, no ISI");
+  static_assert(!PSK || (!ADAPT && !FRAMES), "PSK: one order, single link");
   // ISI: cyclic prefix shorter than the channel memory, or no prefix (channel/models.py:52-55 over the serial stream):
   // the FIR reaches into the previous OFDM symbol.  A team then owns a CONTIGUOUS chain of symbols, carries the last 8
   // tx samples of the previous one in shared memory, and recomputes the transmitter of the symbol before its chain
   // (one "halo" pass), so the result does not depend on how the symbol range is partitioned.
-  static_assert(!ISI || (!ADAPT && !FRAMES), "ISI chains: one order, single link");
+  static_assert(!ISI || !FRAMES, "ISI chains: single link");
   // SC: single-carrier OFDM (modulation/models.py:58-91) - the constellation symbols are the time samples; the
   // receiver runs FFT -> equaliser -> IFFT, i.e. the shared transform body serves phases 1 and 2 instead of 0 and 1
   static_assert(!SC || (!ADAPT && !FRAMES), "SC-OFDM: one order on every sample, single link");

@@ -84,7 +84,7 @@ template <>
 int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
                                                 bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream) {
   constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T;
-  if ((psk && (adapt || sc || isi)) || (adapt && (sc || isi)))
+  if ((psk && adapt) || (adapt && sc))
     return fail(OFDM_EUNSUPPORTED, "this link shape runs on the general kernel");
 #define OFDM_FAST_VARIANT(ADAPT_, SC_, ISI_, PSK_)                                                                     \
   do {                                                                                                                 \
@@ -94,6 +94,22 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
     return L->d.n_taps <= 4 ? launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_, 4>(L, p, stream)         \
                             : launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);           \
   } while (0)
+  // rare combinations: one counters-only kernel (8 evaluated taps) beside the dump-capable ones
+#define OFDM_FAST_RARE(SC_, ISI_, PSK_)                                                                                \
+  do {                                                                                                                 \
+    if (replay) return launch_fast_kernel<E, T, true, true, false, SC_, ISI_, PSK_>(L, p, stream);                     \
+    return dump ? launch_fast_kernel<E, T, true, false, false, SC_, ISI_, PSK_>(L, p, stream)                          \
+                : launch_fast_kernel<E, T, false, false, false, SC_, ISI_, PSK_>(L, p, stream);                        \
+  } while (0)
+  if (adapt && isi) {                                          // per-subcarrier orders / power loading, prefix shorter than the channel memory
+    if (replay) return launch_fast_kernel<E, T, true, true, true, false, true, false>(L, p, stream);
+    return dump ? launch_fast_kernel<E, T, true, false, true, false, true, false>(L, p, stream)
+                : launch_fast_kernel<E, T, false, false, true, false, true, false>(L, p, stream);
+  }
+  if (psk && isi && sc) OFDM_FAST_RARE(true, true, true);      // M-ary PSK on single-carrier symbols with inter-symbol interference
+  if (psk && isi) OFDM_FAST_RARE(false, true, true);           // M-ary PSK, prefix shorter than the channel memory
+  if (psk && sc) OFDM_FAST_RARE(true, false, true);            // M-ary PSK, single-carrier OFDM
+#undef OFDM_FAST_RARE
   if (psk) OFDM_FAST_VARIANT(false, false, false, true);       // M-ary PSK, one order
   if (isi && sc) OFDM_FAST_VARIANT(false, true, true, false);  // SC-OFDM with a prefix shorter than the channel memory
   if (isi) OFDM_FAST_VARIANT(false, false, true, false);       // prefix shorter than the channel memory: chained symbols

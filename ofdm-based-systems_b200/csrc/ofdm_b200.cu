@@ -484,16 +484,14 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
     const bool single_carrier = desc->modulator == OFDM_MOD_SC_OFDM;   // one order, no loading tables
     const bool shape_ok = desc->scheme == OFDM_SCHEME_QAM && (!single_carrier || (uniform_orders(orders, N) && !amp && !rx_gain)) &&
                           Lt <= kFastTaps && fast_supports_n(N) &&
-                          // guard interval at least as long as the channel memory (cyclic or zero-padded), or inter-symbol
-                          // interference with a short cyclic prefix / no prefix: one order, chained symbols
-                          (P >= Lt - 1 ||   /* a one-tap channel needs no guard interval: "no prefix" is then a cyclic prefix of length 0 */
-                           (uniform_orders(orders, N) && !amp && !rx_gain)) &&
+                          // any guard interval: at least as long as the channel memory (cyclic or zero-padded), or shorter / none
+                          // (inter-symbol interference: chained symbols)
                           P < N && !(force && force[0] == '1');
     L->fast = !shape_ok || !loadable ? 0 : (uniform && orders[0] >= 4 && !amp && !rx_gain) ? 1 : 2;
-    // PSK: one order M = 2 .. 256 on every subcarrier, OFDM, guard interval at least as long as the channel memory
+    // PSK: one order M = 2 .. 256 on every subcarrier (OFDM or SC-OFDM, any guard interval: the chained-symbol and the
+    // single-carrier paths do not care how labels become points)
     const bool psk_ok = desc->scheme == OFDM_SCHEME_PSK && uniform && orders[0] >= 2 && orders[0] <= 256 && !amp && !rx_gain &&
-                        desc->modulator == OFDM_MOD_OFDM && P >= Lt - 1 && P < N &&
-                        Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1');
+                        P < N && Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1');
     if (psk_ok) L->fast = 3;
     if (L->fast) {
       const double sqn = std::sqrt((double)N);
@@ -524,13 +522,15 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
         }
       }
       if (L->fast == 3) {
-        // PSK tables: A = H / sqrt(N) (receiver transform), label -> exp(j 2 pi gray^-1(label) / M)
+        // PSK tables: A = H / sqrt(N) (receiver transform; H / N for SC-OFDM, whose second transform is unnormalised too),
+        // label -> exp(j 2 pi gray^-1(label) / M)
         const int M = orders[0];
+        const double rxn = single_carrier ? double(N) : sqn;
         for (int k = 0; k < N; ++k) {
           const std::complex<double> H(h_eq[2 * k], h_eq[2 * k + 1]);
-          if (desc->equalizer == OFDM_EQ_NONE) eqf[k] = make_float4((float)(1.0 / sqn), 0.f, 1.f, 0.f);
-          else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) eqf[k] = make_float4((float)(1e10 / sqn), 0.f, 1.f, 0.f);
-          else eqf[k] = make_float4((float)(H.real() / sqn), (float)(H.imag() / sqn), (float)std::norm(H), 0.f);
+          if (desc->equalizer == OFDM_EQ_NONE) eqf[k] = make_float4((float)(1.0 / rxn), 0.f, 1.f, 0.f);
+          else if (desc->equalizer == OFDM_EQ_ZF && H == std::complex<double>(0.0, 0.0)) eqf[k] = make_float4((float)(1e10 / rxn), 0.f, 1.f, 0.f);
+          else eqf[k] = make_float4((float)(H.real() / rxn), (float)(H.imag() / rxn), (float)std::norm(H), 0.f);
         }
         psk_host.assign(256, make_float2(1.f, 0.f));
         for (int lab = 0; lab < M; ++lab) {

@@ -135,6 +135,13 @@ VARIANTS = [
     # the 4-tap instantiations of the loading and the chained-symbol kernels (the dump-capable twin evaluates 8 taps)
     ("adaptive_4taps", 64, 0, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "OFDM", True),
     ("isi_4taps", 64, 64, "QAM", "Lin-Phoong_P2", "CYCLIC", 1, "MMSE", "OFDM", False),
+    # combinations that ran on the general kernel until the end of round 2: PSK on single-carrier symbols, PSK or loading
+    # tables with a prefix shorter than the channel memory
+    ("psk_sc", 256, 8, "PSK", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "SC-OFDM", False),
+    ("psk_isi", 128, 16, "PSK", "severe_multipath", "CYCLIC", 2, "ZF", "OFDM", False),
+    ("psk_sc_isi", 64, 16, "PSK", "rayleigh_fading", "NONE", 0, "MMSE", "SC-OFDM", False),
+    ("adaptive_isi", 512, 0, "QAM", "severe_multipath", "CYCLIC", 3, "MMSE", "OFDM", True),
+    ("adaptive_isi_zp", 64, 0, "QAM", "rayleigh_fading", "ZERO", 2, "MMSE", "OFDM", True),
 ]
 
 
