@@ -58,7 +58,7 @@ def _units():
     if os.path.exists(os.path.join(CSRC, "link_fast.cu")):
         units.append(("link_fast", os.path.join(CSRC, "link_fast.cu"), []))
     if os.path.exists(os.path.join(CSRC, "link_fast_inst.cu")):
-        for e, t in ((8, 8), (8, 16), (16, 16), (16, 32), (32, 32), (32, 64), (32, 128)):
+        for e, t in ((8, 8), (8, 16), (16, 16), (16, 32), (32, 32), (32, 64), (32, 128), (32, 256)):
             units.append((f"link_fast_inst_{e}x{t}", os.path.join(CSRC, "link_fast_inst.cu"),
                           [f"-DOFDM_FAST_E={e}", f"-DOFDM_FAST_T={t}"]))
     for n in SIZES:

@@ -179,7 +179,7 @@ int frames_run_impl(const ofdm_frames_desc* d, const double* taps, int64_t n_fra
                     ofdm_link_result* per_frame, int32_t* orders_out, double* taps_out, const FrameTableDump* dump) {
   if (!d || !total) return fail(OFDM_EINVAL, "null argument");
   const int N = d->n_subcarriers, L = d->n_taps, P = d->prefix_len;
-  if (!fast_supports_n(N)) return fail(OFDM_EUNSUPPORTED, "frame batches need n_subcarriers = a power of two in 64..4096, got %d", N);
+  if (!fast_supports_n(N)) return fail(OFDM_EUNSUPPORTED, "frame batches need n_subcarriers = a power of two in 64..8192, got %d", N);
   if (L < 1 || L > kFastTaps) return fail(OFDM_EUNSUPPORTED, "frame batches need 1..%d taps, got %d", kFastTaps, L);
   if (P < L - 1 || P >= N) return fail(OFDM_EUNSUPPORTED, "frame batches need a cyclic prefix with n_taps - 1 <= prefix_len < N");
   if (d->equalizer < 0 || d->equalizer > 2) return fail(OFDM_EINVAL, "equalizer=%d", d->equalizer);

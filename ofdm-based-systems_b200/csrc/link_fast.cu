@@ -23,6 +23,7 @@ int launch_fast_frames(int n_subcarriers, int sms, const FastParams& p, cudaStre
     case 1024: return launch_frames_shape<32, 32>(sms, p, stream);
     case 2048: return launch_frames_shape<32, 64>(sms, p, stream);
     case 4096: return launch_frames_shape<32, 128>(sms, p, stream);
+    case 8192: return launch_frames_shape<32, 256>(sms, p, stream);
     default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", n_subcarriers);
   }
 }
@@ -48,7 +49,13 @@ std::vector<float2> build_fast_twiddles(int N) {
   return tw;
 }
 
-bool fast_supports_n(int n) { return n >= 64 && n <= 4096 && (n & (n - 1)) == 0; }
+bool fast_supports_n(int n) { return n >= 64 && n <= 8192 && (n & (n - 1)) == 0; }
+// which combinations of the kernel's flags are instantiated for a transform size (link_fast_inst.cu)
+bool fast_supports_combo(int n, bool adapt, bool sc, bool isi, bool psk) {
+  if ((psk && adapt) || (adapt && sc)) return false;
+  if (n >= 2048 && psk && (sc || isi)) return false;
+  return true;
+}
 int fast_samples_per_lane(int n) { return n <= 128 ? 8 : n <= 512 ? 16 : 32; }
 
 int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay, bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream) {
@@ -60,6 +67,7 @@ int launch_fast(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
     case 1024: return launch_fast_shape<32, 32>(L, p, dump, replay, adapt, sc, isi, psk, stream);
     case 2048: return launch_fast_shape<32, 64>(L, p, dump, replay, adapt, sc, isi, psk, stream);
     case 4096: return launch_fast_shape<32, 128>(L, p, dump, replay, adapt, sc, isi, psk, stream);
+    case 8192: return launch_fast_shape<32, 256>(L, p, dump, replay, adapt, sc, isi, psk, stream);
     default: return fail(OFDM_EUNSUPPORTED, "no fast plan for n_subcarriers=%d", L->d.n_subcarriers);
   }
 }

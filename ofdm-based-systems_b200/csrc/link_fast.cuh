@@ -107,10 +107,13 @@ struct FastParams {
 
 template <int E, int T_ = E, int BLOCK_ = 512>
 struct FastGeometry {
-  static_assert(T_ % E == 0 && (T_ / E == 1 || T_ / E == 2 || T_ / E == 4) && (T_ <= 32 || T_ % 32 == 0), "team shape");
+  static_assert(T_ % E == 0 && (T_ / E == 1 || T_ / E == 2 || T_ / E == 4 || T_ / E == 8) && (T_ <= 32 || T_ % 32 == 0), "team shape");
   static constexpr int T = T_;                // lanes per OFDM symbol
   static constexpr int N = E * T;
   static constexpr int W = T / E;             // radix of the third pass (1: two-pass transform)
+  // the equaliser table (16 N bytes) sits in shared memory beside the teams' buffers up to N = 4096; at N = 8192 (two teams of
+  // eight warps, 139 KB of sample buffers) it is read through the read-only data path instead
+  static constexpr bool EQ_SMEM = N <= 4096;
   static constexpr int RS = E + 2;            // row stride (complex): conflict-free 128-bit row accesses
   // float2 per team: T rows of E samples; teams narrower than a half-warp are offset by half a bank cycle (64 B) so that
   // the 64-bit column accesses of the two teams of a half-warp fall on different banks (ncu: 2-way conflicts on every
@@ -124,7 +127,7 @@ struct FastGeometry {
   static constexpr int RED_F = T > 32 ? TEAMS * (T / 32) : 0;   // cross-warp reduction scratch (floats)
   static constexpr int TAIL_F2 = 8;           // ISI: last tx samples of the previous OFDM symbol, per team
   static constexpr int PSK_F2 = 256;          // PSK: point table
-  static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(N) * sizeof(float4) +
+  static constexpr size_t SMEM_BYTES = (size_t(TEAMS) * TEAM_F2 + TW_F2) * sizeof(float2) + size_t(EQ_SMEM ? N : 0) * sizeof(float4) +
                                        RED_F * sizeof(float) + (size_t(TEAMS) * TAIL_F2 + PSK_F2) * sizeof(float2);
 };
 
@@ -354,8 +357,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   float2* row = buf + t * RS;
   float2* s_tw = smem2 + size_t(G::TEAMS) * G::TEAM_F2;
   float4* s_eq = reinterpret_cast<float4*>(s_tw + G::TW_F2);
-  float* s_red = reinterpret_cast<float*>(s_eq + N) + team_in_block * (T / 32);
-  float2* s_tail = reinterpret_cast<float2*>(reinterpret_cast<float*>(s_eq + N) + G::RED_F) + team_in_block * G::TAIL_F2;
+  float* s_red = reinterpret_cast<float*>(s_eq + (G::EQ_SMEM ? N : 0)) + team_in_block * (T / 32);
+  float2* s_tail = reinterpret_cast<float2*>(reinterpret_cast<float*>(s_eq + (G::EQ_SMEM ? N : 0)) + G::RED_F) + team_in_block * G::TAIL_F2;
   float2* s_psk = s_tail - team_in_block * G::TAIL_F2 + G::TEAMS * G::TAIL_F2;
   float2* col = buf + trow * RS + tcol;   // strided set: col[W * RS * m]
   auto tsync = [&]() { team_sync<T>(team_in_block); };
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   // block-resident copies of the twiddle and equaliser tables
   for (int i = threadIdx.x; i < G::TW_F2; i += BLOCK) s_tw[i] = __ldg(&p.tw[i]);
   if constexpr (!FRAMES) {
-    for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[i]);
+    for (int i = threadIdx.x; i < (G::EQ_SMEM ? N : 0); i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[i]);
   }
   if constexpr (PSK) {
     for (int i = threadIdx.x; i < G::PSK_F2; i += BLOCK) s_psk[i] = __ldg(&p.psk_tab[i]);
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
   float noise_c2 = FRAMES ? 0.f : -1.3862943611198906f * p.point_tab[blockIdx.y].sigma * p.point_tab[blockIdx.y].sigma;   // -2 sigma^2 ln 2
   [[maybe_unused]] float noise_c2m = -32.000003814697266f * noise_c2;   // see noise20_radius()
   const float2* level_tab = p.level_tab;
+  [[maybe_unused]] const float4* eq_g = p.eq_tab;   // !EQ_SMEM: this block's equaliser table in global memory
   __shared__ FrameHeader s_hdr;
   [[maybe_unused]] unsigned long long unit = blockIdx.x;
   [[maybe_unused]] long long cur_frame = -1;
@@ -503,7 +507,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
     if ((long long)f != cur_frame) {
       // the whole block moves to frame f: its equaliser table and header into shared memory, masks into registers
       __syncthreads();
-      for (int i = threadIdx.x; i < N; i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[f * N + i]);
+      for (int i = threadIdx.x; i < (G::EQ_SMEM ? N : 0); i += BLOCK) s_eq[i] = __ldg(&p.eq_tab[f * N + i]);
+      eq_g = p.eq_tab + f * N;
       if (threadIdx.x < (int)(sizeof(FrameHeader) / sizeof(float)))
         reinterpret_cast<float*>(&s_hdr)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(&p.frame_hdr[f]) + threadIdx.x);
       __syncthreads();
@@ -1020,6 +1025,36 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
           };
           if constexpr (W == 2) {
             fused(u[q], u[q + Q], w1);
+          } else if constexpr (W == 8) {
+            // radix 8 as three radix-2 steps on x_r = u[q + r Q]: X_k = sum_r x_r w^r omega8^(r k).  Step 1 pairs (r, r + 4)
+            // with w^4; the even outputs are then a radix-4 transform of the sums with base twiddle w, the odd ones of the
+            // differences with base w omega8; steps 2 and 3 are the radix-4 recipe below for both halves.  Results sit in
+            // bit-reversed positions and are renamed into natural order.
+            constexpr float h = 0.70710678118654752440f;
+            const float2 w2 = cmul(w1, w1), w4 = cmul(w2, w2);
+            const float2 w8 = make_float2((w1.x + w1.y) * h, (w1.y - w1.x) * h);   // w omega8, omega8 = (1 - j) / sqrt 2
+            auto mj = [](float2 z) { return make_float2(z.y, -z.x); };            // -j z
+            float2 x[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) x[r] = u[q + r * Q];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) fused(x[r], x[r + 4], w4);
+            fused(x[0], x[2], w2);
+            fused(x[1], x[3], w2);
+            fused(x[4], x[6], mj(w2));
+            fused(x[5], x[7], mj(w2));
+            fused(x[0], x[1], w1);
+            fused(x[2], x[3], mj(w1));
+            fused(x[4], x[5], w8);
+            fused(x[6], x[7], mj(w8));
+            u[q] = x[0];
+            u[q + Q] = x[4];
+            u[q + 2 * Q] = x[2];
+            u[q + 3 * Q] = x[6];
+            u[q + 4 * Q] = x[1];
+            u[q + 5 * Q] = x[5];
+            u[q + 6 * Q] = x[3];
+            u[q + 7 * Q] = x[7];
           } else {
             // radix 4 as two radix-2 steps: with w3 = w1 w2, w1 a1 +- w3 a3 = w1 (a1 +- w2 a3), so the legs need w2 first and
             // w1 (times 1 or -j) in the second step: X0,2 = (a0 + w2 a2) +- w1 (a1 + w2 a3), X1,3 = (a0 - w2 a2) -+ j w1 (a1 - w2 a3)
@@ -1059,7 +1094,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         for (int m = 0; m < E; ++m) {
           const float2 yv = u[oidx(m)];
           const int k = t + T * m;
-          const float4 e = s_eq[k];
+          const float4 e = G::EQ_SMEM ? s_eq[k] : __ldg(&eq_g[k]);
           const float a = fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
           const float b = fmaf(yv.x, e.y, -yv.y * e.x);   // -Im(Y conj A)
           const float inv = fast_rcp(e.z + sigma2);
@@ -1097,7 +1132,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ofdm_link_fast_kernel(const __gri
         for (int m = 0; m < E; ++m) {
           const float2 yv = u[oidx(m)];
           const int k = t + T * m;
-          const float4 e = s_eq[k];
+          const float4 e = G::EQ_SMEM ? s_eq[k] : __ldg(&eq_g[k]);
           // SC: yv = swap(z~) of time sample k, already equalised and scaled for the slicer
           const float a = SC ? yv.y : fmaf(yv.x, e.x, yv.y * e.y);    //  Re(Y conj A)
           const float b = SC ? -yv.x : fmaf(yv.x, e.y, -yv.y * e.x);  // -Im(Y conj A)

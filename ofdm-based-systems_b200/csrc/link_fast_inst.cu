@@ -84,15 +84,21 @@ template <>
 int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastParams& p, bool dump, bool replay,
                                                 bool adapt, bool sc, bool isi, bool psk, cudaStream_t stream) {
   constexpr int E = OFDM_FAST_E, T = OFDM_FAST_T;
-  if ((psk && adapt) || (adapt && sc))
+  // Teams wider than a warp (N >= 2048) carry fewer instantiations - they are 4 MB of SASS per shape: every channel is
+  // evaluated with 8 taps, and M-PSK combined with SC-OFDM or inter-symbol interference stays on the general kernel
+  // (fast_supports_combo() below tells ofdm_link_create, which decides the kernel of a link).
+  constexpr bool kWide = T >= 64;
+  if ((psk && adapt) || (adapt && sc) || !fast_supports_combo(E * T, adapt, sc, isi, psk))
     return fail(OFDM_EUNSUPPORTED, "this link shape runs on the general kernel");
 #define OFDM_FAST_VARIANT(ADAPT_, SC_, ISI_, PSK_)                                                                     \
   do {                                                                                                                 \
     if (replay) return launch_fast_kernel<E, T, true, true, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                    \
     if (dump) return launch_fast_kernel<E, T, true, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                     \
     /* channels of at most 4 taps (every shipped model but two): the FIR skips the four exact zeros */                 \
-    return L->d.n_taps <= 4 ? launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_, 4>(L, p, stream)         \
-                            : launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);           \
+    if constexpr (!kWide) {                                                                                            \
+      if (L->d.n_taps <= 4) return launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_, 4>(L, p, stream);   \
+    }                                                                                                                  \
+    return launch_fast_kernel<E, T, false, false, ADAPT_, SC_, ISI_, PSK_>(L, p, stream);                              \
   } while (0)
   // rare combinations: one counters-only kernel (8 evaluated taps) beside the dump-capable ones
 #define OFDM_FAST_RARE(SC_, ISI_, PSK_)                                                                                \
@@ -106,9 +112,11 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
     return dump ? launch_fast_kernel<E, T, true, false, true, false, true, false>(L, p, stream)
                 : launch_fast_kernel<E, T, false, false, true, false, true, false>(L, p, stream);
   }
-  if (psk && isi && sc) OFDM_FAST_RARE(true, true, true);      // M-ary PSK on single-carrier symbols with inter-symbol interference
-  if (psk && isi) OFDM_FAST_RARE(false, true, true);           // M-ary PSK, prefix shorter than the channel memory
-  if (psk && sc) OFDM_FAST_RARE(true, false, true);            // M-ary PSK, single-carrier OFDM
+  if constexpr (!kWide) {
+    if (psk && isi && sc) OFDM_FAST_RARE(true, true, true);    // M-ary PSK on single-carrier symbols with inter-symbol interference
+    if (psk && isi) OFDM_FAST_RARE(false, true, true);         // M-ary PSK, prefix shorter than the channel memory
+    if (psk && sc) OFDM_FAST_RARE(true, false, true);          // M-ary PSK, single-carrier OFDM
+  }
 #undef OFDM_FAST_RARE
   if (psk) OFDM_FAST_VARIANT(false, false, false, true);       // M-ary PSK, one order
   if (isi && sc) OFDM_FAST_VARIANT(false, true, true, false);  // SC-OFDM with a prefix shorter than the channel memory
@@ -116,12 +124,20 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   if (sc) OFDM_FAST_VARIANT(false, true, false, false);        // single-carrier OFDM: one order on every sample
   if (adapt) OFDM_FAST_VARIANT(true, false, false, false);     // per-subcarrier orders / applied power loading
 #undef OFDM_FAST_VARIANT
-  if (replay) return dump ? launch_fast_kernel<E, T, true, true>(L, p, stream) : launch_fast_kernel<E, T, false, true>(L, p, stream);
+  if (replay) {   // the counters-only recorded-stream kernel is the HBM-bandwidth benchmark of the narrow shapes
+    if constexpr (!kWide) {
+      if (!dump) return launch_fast_kernel<E, T, false, true>(L, p, stream);
+    }
+    return launch_fast_kernel<E, T, true, true>(L, p, stream);
+  }
   // the dump-capable kernel evaluates the FIR in the same form as the counters-only kernel of the link (plain complex
   // product for one tap, Gauss form otherwise), so that the two return identical counters
-  if (dump)
-    return L->d.n_taps <= 1 ? launch_fast_kernel<E, T, true, false, false, false, false, false, 1, 0, kOptOneTap>(L, p, stream)
-                            : launch_fast_kernel<E, T, true, false>(L, p, stream);
+  if (dump) {
+    if constexpr (!kWide) {
+      if (L->d.n_taps <= 1) return launch_fast_kernel<E, T, true, false, false, false, false, false, 1, 0, kOptOneTap>(L, p, stream);
+    }
+    return launch_fast_kernel<E, T, true, false>(L, p, stream);
+  }
   // The warps of a block run free (SYNC = 0).  Round 1 aligned the warps that share a scheduler at the section
   // boundaries (named barrier per scheduler, SYNC = 2): they then share instruction fetches (stall_no_instruction 0.16
   // instead of 0.49 per issue) but meet the shared-memory exchanges and the MUFU section together.  With the round-2
@@ -132,12 +148,14 @@ int launch_fast_shape<OFDM_FAST_E, OFDM_FAST_T>(const ofdm_link* L, const FastPa
   // product (4 FFMA) beats the Gauss form (3 FFMA + 3 FADD)
   constexpr int kZf = kOptDefault | kOptNoEstimate;
   const bool mmse = L->d.equalizer == OFDM_EQ_MMSE;
-  if (L->d.n_taps <= 1)
-    return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptOneTap>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptOneTap | kOptNoEstimate>(L, p, stream);
-  if (L->d.n_taps <= 4)
-    return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 4>(L, p, stream)
-                : launch_fast_kernel<E, T, false, false, false, false, false, false, 4, S, kZf>(L, p, stream);
+  if constexpr (!kWide) {
+    if (L->d.n_taps <= 1)
+      return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptOneTap>(L, p, stream)
+                  : launch_fast_kernel<E, T, false, false, false, false, false, false, 1, S, kOptOneTap | kOptNoEstimate>(L, p, stream);
+    if (L->d.n_taps <= 4)
+      return mmse ? launch_fast_kernel<E, T, false, false, false, false, false, false, 4>(L, p, stream)
+                  : launch_fast_kernel<E, T, false, false, false, false, false, false, 4, S, kZf>(L, p, stream);
+  }
   return mmse ? launch_fast_kernel<E, T, false, false>(L, p, stream)
               : launch_fast_kernel<E, T, false, false, false, false, false, false, 8, S, kZf>(L, p, stream);
 }

@@ -491,7 +491,8 @@ int ofdm_link_create_loaded(const ofdm_link_desc* desc, const double* taps_chan,
     // PSK: one order M = 2 .. 256 on every subcarrier (OFDM or SC-OFDM, any guard interval: the chained-symbol and the
     // single-carrier paths do not care how labels become points)
     const bool psk_ok = desc->scheme == OFDM_SCHEME_PSK && uniform && orders[0] >= 2 && orders[0] <= 256 && !amp && !rx_gain &&
-                        P < N && Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1');
+                        P < N && Lt <= kFastTaps && fast_supports_n(N) && !(force && force[0] == '1') &&
+                        fast_supports_combo(N, false, single_carrier, Lt - 1 > P, true);
     if (psk_ok) L->fast = 3;
     if (L->fast) {
       const double sqn = std::sqrt((double)N);

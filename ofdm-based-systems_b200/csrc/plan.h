@@ -87,6 +87,7 @@ template <int N> int launch_kernel(const ofdm_link* L, const LinkParams& p, cuda
 namespace ofdm {
 struct FastParams;
 bool fast_supports_n(int n);
+bool fast_supports_combo(int n, bool adapt, bool sc, bool isi, bool psk);   // link_fast.cu
 int fast_samples_per_lane(int n);
 }  // namespace ofdm
 #include <vector>

@@ -16,7 +16,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 bad = 0
 fast_count = 0
 for case in range(cases):
-    n = int(rng.choice([64, 128, 256, 512, 1024, 2048, 4096], p=[.25, .1, .2, .1, .2, .05, .1]))
+    n = int(rng.choice([64, 128, 256, 512, 1024, 2048, 4096, 8192], p=[.25, .1, .2, .1, .17, .05, .08, .05]))
     scheme = "PSK" if rng.random() < 0.2 else "QAM"
     order = int(rng.choice([2, 4, 8, 16, 32, 64]) if scheme == "PSK" else rng.choice([4, 16, 64, 256]))
     L = int(rng.integers(1, 9))

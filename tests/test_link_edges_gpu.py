@@ -120,7 +120,8 @@ VARIANTS = [
     ("isi_wide", 2048, 64, "QAM", "severe_multipath", "NONE", 0, "ZF", "OFDM", False),
     ("psk", 1024, 8, "PSK", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),
     ("adaptive", 1024, 0, "QAM", "severe_multipath", "CYCLIC", 7, "MMSE", "OFDM", True),
-    ("general", 8192, 16, "QAM", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),
+    ("general", 32, 16, "QAM", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),        # N < 64: the general kernel
+    ("widest", 8192, 16, "QAM", "two_ray", "CYCLIC", 1, "MMSE", "OFDM", False),        # two teams of eight warps, radix-8 third pass
     # the headline shape's short-channel instantiations (1 and 4 evaluated taps) and the small transforms of the shipped configs
     ("flat", 64, 16, "QAM", "flat_fading", "CYCLIC", 16, "ZF", "OFDM", False),
     ("four_taps", 64, 64, "QAM", "Lin-Phoong_P1", "CYCLIC", 3, "MMSE", "OFDM", False),

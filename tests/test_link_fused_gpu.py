@@ -56,7 +56,7 @@ def test_fused_dump_replays_through_oracle(case, kat):
     sigma = float(np.sqrt(1.0 / 10 ** (snr / 10) / 2))
     link = Link(n, setup.taps_chan, setup.H_eq, np.full(n, order), prefix_type=prefix, prefix_len=P,
                 modulator=modulator, equalizer=eq, scheme=scheme)
-    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512", "sc", "sc4096", "zp", "zp1024", "isi", "none", "isi1024", "psk", "psk64", "bpsk"))
+    assert link.uses_fast_kernel == (name in ("headline", "c1", "c2", "c5", "n2048", "n2048zf", "n128", "n512", "sc", "sc4096", "zp", "zp1024", "isi", "none", "isi1024", "psk", "psk64", "bpsk", "n8192"))
     # with inter-symbol interference the oracle's stream must start where the kernel's does (zero history)
     first = 0 if len(taps_raw) - 1 > P else 1000
     res, d = link.run_fused(snr, sigma, n_ofdm, seed=1234, point=3, first_symbol=first,
@@ -85,7 +85,8 @@ ADAPTIVE_CASES = [
     ("a4096", 4096, "rayleigh_fading", 5, "MMSE", 28.0, 8, True),
     ("a128", 128, "two_ray", 1, "MMSE", 20.0, 32, True),
     ("a512", 512, "Lin-Phoong_P2", 3, "ZF", 25.0, 16, True),
-    ("a8192", 8192, "two_ray", 1, "MMSE", 20.0, 2, False),
+    ("a8192", 8192, "two_ray", 1, "MMSE", 20.0, 2, True),
+    ("a32", 32, "two_ray", 1, "MMSE", 20.0, 40, False),
 ]
 
 
@@ -170,7 +171,7 @@ def test_sharding_is_invariant(kat):
 
 
 @pytest.mark.parametrize("n,chan,P,eq,fast", [(64, "Lin-Phoong_P2", 3, "ZF", True), (1024, "severe_multipath", 7, "MMSE", True),
-                                              (128, "rayleigh_fading", 5, "MMSE", True), (8192, "two_ray", 1, "ZF", False)])
+                                              (128, "rayleigh_fading", 5, "MMSE", True), (8192, "two_ray", 1, "ZF", True), (32, "two_ray", 1, "ZF", False)])
 def test_applied_power_loading_replays_through_oracle(n, chan, P, eq, fast, kat):
     """water-filling power APPLIED at the transmitter (sqrt(P_k) on every subcarrier) and compensated at
     the receiver (1/sqrt(P_k)), as examples/waterfilling_noise_bump_experiment.py:148,165-169 does around the
