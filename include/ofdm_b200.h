@@ -211,7 +211,7 @@ int ofdm_waterfill_bitload_batched_dev(const ofdm_waterfill_desc* desc, const do
 
 /* Frame batches: `n_frames` channel realisations, `symbols_per_frame` OFDM symbols each, in one launch of the link
  * kernel (what the reference would run as one Simulation per realisation, simulation/models.py:155-212, :454-606).
- * OFDM modulator, QAM, cyclic prefix >= channel memory, <= 8 taps, N a power of two in 64 .. 4096. */
+ * OFDM modulator, QAM, cyclic prefix >= channel memory, <= 8 taps, N a power of two in 64 .. 8192. */
 typedef struct ofdm_frames_desc {
   int32_t n_subcarriers;
   int32_t prefix_len;

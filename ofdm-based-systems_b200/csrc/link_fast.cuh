@@ -1,6 +1,6 @@
 // ofdm_link_fast kernel: the Monte-Carlo hot loop, <= 8 channel taps, N = E*T subcarriers: a team of T lanes with
-//   E samples per lane.  T = E in {8, 16, 32} (N = 64, 256, 1024: two-pass transform); T = 2E or 4E (N = 128, 512
-//   inside a warp; N = 2048, 4096 with a team of 2 or 4 warps): a third radix-2/4 pass follows a second exchange.
+//   E samples per lane.  T = E in {8, 16, 32} (N = 64, 256, 1024: two-pass transform); T = 2E, 4E or 8E (N = 128, 512
+//   inside a warp; N = 2048, 4096, 8192 with a team of 2, 4 or 8 warps): a third radix-2/4/8 pass follows a second exchange.
 //   The headline instantiation is OFDM, one square-QAM order (4 .. 256), cyclic prefix >= channel memory, Philox bits
 //   and noise; compile-time flags add, each in its own instantiation so that the headline stream stays untouched:
 //     REPLAY  recorded bits and noise streamed from HBM          ADAPT   per-subcarrier orders / applied power loading
