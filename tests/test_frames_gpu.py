@@ -76,7 +76,7 @@ def test_device_built_frame_tables_equal_the_host_built_link_tables(n, order, eq
 
 
 @pytest.mark.parametrize("n,order,eq,S", [(64, 16, "ZF", 100), (128, 4, "MMSE", 70), (256, 64, "MMSE", 37), (512, 16, "NONE", 33), (1024, 64, "MMSE", 20),
-                                          (4096, 256, "MMSE", 9)])
+                                          (4096, 256, "MMSE", 9), (8192, 64, "MMSE", 5)])
 def test_fixed_order_frames_reproduce_single_links(n, order, eq, S):
     from ofdm_based_systems._native import run_frames
     rng = np.random.default_rng(n)
