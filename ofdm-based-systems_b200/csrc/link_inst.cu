@@ -25,7 +25,7 @@ template <int N>
 int launch_kernel(const ofdm_link* L, const LinkParams& p, cudaStream_t stream) {
   constexpr int E = elements_per_thread(N);
   using G = Geometry<N, E>;
-  const unsigned long long need = (p.sym_count + G::TEAMS - 1) / G::TEAMS;
+  const unsigned long long need = (p.sym_count - p.sym_lo + G::TEAMS - 1) / G::TEAMS;
   unsigned long long grid = (unsigned long long)L->sms * L->occ;
   if (need < grid) grid = need;
   if (grid == 0) return OFDM_OK;

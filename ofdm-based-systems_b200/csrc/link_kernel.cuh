@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(Geometry<N, E>::BLOCK) ofdm_link_kernel(const 
   // contiguous chunk of OFDM symbols for this team (needed for the ISI chain)
   const unsigned long long n_teams = (unsigned long long)gridDim.x * G::TEAMS;
   const unsigned long long team_id = (unsigned long long)blockIdx.x * G::TEAMS + team.team_in_block;
-  const unsigned long long per = (p.sym_count + n_teams - 1) / n_teams;
-  unsigned long long s0 = team_id * per, s1 = s0 + per;
+  const unsigned long long per = (p.sym_count - p.sym_lo + n_teams - 1) / n_teams;
+  unsigned long long s0 = p.sym_lo + team_id * per, s1 = s0 + per;
   if (s0 > p.sym_count) s0 = p.sym_count;
   if (s1 > p.sym_count) s1 = p.sym_count;
 

@@ -32,6 +32,7 @@ struct LinkParams {
   unsigned int point;     // SNR-point index, part of the Philox counter
   unsigned int bits_per_ofdm;
   unsigned long long sym_begin, sym_count;  // global index of this launch's first OFDM symbol, count
+  unsigned long long sym_lo;                // first symbol (relative to sym_begin and to the replay buffers) this launch processes
   // ---- replay inputs (indexed by symbol - sym_begin)
   const unsigned char* bits;
   unsigned long long bits_len;

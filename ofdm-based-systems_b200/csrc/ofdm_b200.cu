@@ -783,8 +783,28 @@ int ofdm_link_launch_replay(ofdm_link* L, double snr_db, const uint8_t* bits_dev
     return launch_fast(L, f, dump_dev != nullptr, true, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0, L->fast == 3,
                        (cudaStream_t)stream);
   }
+  // Ragged recorded stream on a fast-kernel link (the comparison ends inside the LAST OFDM symbol, zip() truncation of
+  // simulation/models.py:597): the whole symbols before it stream through the fast kernel, the last one runs on the
+  // general kernel, which masks the bits past the limit; both add into the link's counter block.
+  unsigned long long general_from = 0;
+  if (L->fast != 0 && !L->d_post && n_symbols >= 2 && compare_limit_bits != 0 && compare_limit_bits < whole &&
+      compare_limit_bits > whole - (uint64_t)L->bits_per_ofdm && n_bytes * 8 >= whole - (uint64_t)L->bits_per_ofdm &&
+      (reinterpret_cast<uintptr_t>(bits_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(noise_dev) & 15) == 0) {
+    FastParams f;
+    fill_fast(L, f, snr_db, dump_dev);
+    f.bits = bits_dev;
+    f.bits_len = n_bytes;
+    f.noise = noise_dtype == OFDM_NOISE_NONE ? nullptr : noise_dev;
+    f.noise_f64 = noise_dtype == OFDM_NOISE_C128;
+    f.sym_count = n_symbols - 1;
+    const int rc_fast = launch_fast(L, f, dump_dev != nullptr, true, L->fast == 2, L->d.modulator == OFDM_MOD_SC_OFDM, L->isi != 0,
+                                    L->fast == 3, (cudaStream_t)stream);
+    if (rc_fast) return rc_fast;
+    general_from = n_symbols - 1;
+  }
   LinkParams p;
   fill_params(L, p, snr_db);
+  p.sym_lo = general_from;
   p.bits_src = SRC_REPLAY_F32;
   p.noise_src = noise_dtype;
   p.bits = bits_dev;

@@ -39,8 +39,12 @@ def test_ragged_recorded_stream(kernel, monkeypatch):
     full = rng.integers(0, 256, n_sym * bits_per // 8, dtype=np.uint8)
     cut = full[: len(full) - 100]                                     # 800 bits short
     noise = (rng.normal(size=n_sym * 1031) + 1j * rng.normal(size=n_sym * 1031)) * 0.05
+    from ofdm_based_systems import _native
     whole = link.run_replay(20.0, full.tobytes(), noise, n_sym)
+    before = _native.launch_count()
     ragged = link.run_replay(20.0, cut.tobytes(), noise, n_sym, compare_limit_bits=8 * len(cut))
+    # a fast-kernel link streams the whole symbols through the fast kernel and runs only the last one on the general kernel
+    assert _native.launch_count() - before == (2 if kernel == "auto" else 1)
     assert whole.bits == n_sym * bits_per and ragged.bits == 8 * len(cut)
     assert ragged.bit_errors <= whole.bit_errors + 40                 # the zero-filled tail changes only the last symbol
     none = link.run_replay(20.0, full.tobytes(), None, n_sym)
